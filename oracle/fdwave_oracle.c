@@ -1,0 +1,587 @@
+/*
+ * fdwave_oracle.c -- CPU restatement of the reference's finite-difference
+ * acoustic propagation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (the CUDA library, the
+ * Python package, the C drivers under apps/) may include, link or call this
+ * file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and only as the checker / CPU baseline.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this file
+ *   - bit-exactly against dpct_migrated_stencil_computation/output_teste.bin,
+ *   - bit-exactly against dpct_gpu_rtm_domain_division/build/3lay_mod/
+ *     {dobs.bin, dir.img, dir.image},
+ *   - to rel-L2 <= 2e-5 against cuda_reference_stencil_computation/input.bin
+ *     (the reference's own forward snapshot),
+ *   - bit-exactly, function by function, against the reference's own objects
+ *     compiled into oracle/_ref/ (tests/test_oracle_vs_ref.py).
+ *
+ * All arrays are flat float32, logical shape [nxe][nze], z fastest -- the
+ * layout of the reference's alloc2float(nze,nxe) blocks
+ * (cuda_reference_RTM/lib/src/functions.c:168-182).
+ *
+ * Two arithmetic "families" exist in the reference and both are restated:
+ *   G  = GPU family   (cuda_reference_RTM/src/fd-code.cu, lib/src/functions.c;
+ *        identical arithmetic in the dpct_migrated_* SYCL sources)
+ *   C  = CPU family   (dpct_gpu_rtm_domain_division/src/...)
+ *
+ * Compile with -ffp-contract=off and without -ffast-math: the absence of FMA
+ * contraction is part of the bit pattern (reference: nvcc --fmad=false,
+ * cuda_reference_RTM/Makefile:4; g++ -O3 on baseline x86-64,
+ * dpct_gpu_rtm_domain_division/src/Makefile:6-7).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_PI (3.141592653589793) /* functions.h:7, cwp.h:126 */
+#define ORC_SIZEBLOCK 8            /* cuda_reference_RTM/lib/include/functions.h:6 */
+
+static int g_threads = 1;
+
+/* number of OpenMP threads used by the sweep loops (1 = serial, as the
+ * reference's CPU family is: its sources carry no OpenMP pragma). */
+void orc_set_threads(int n)
+{
+    g_threads = n < 1 ? 1 : n;
+#ifdef _OPENMP
+    omp_set_num_threads(g_threads);
+#endif
+}
+
+int orc_get_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ */
+/* Host tables                                                          */
+/* ------------------------------------------------------------------ */
+
+/* windowed-sinc generator for orders outside {2,4,6,8}.
+ * family 0 (G): functions.c:125-157 compiled as C  -> double cos/pow.
+ * family 1 (C): fd.c:99-130 compiled as C++ by g++ -> cosf/powf.        */
+static void orc_makeo2(float *coef, int order, int family)
+{
+    float alpha = .54, beta = 6.;
+    float h_beta = 0.5 * beta;
+    float alpha1 = 2. * alpha - 1.0;
+    float alpha2 = 2. * (1.0 - alpha);
+    float central = 0.0, filt, arg, wind;
+    int sign = -1, half = order / 2;
+    for (int k = 1; k <= half; k++) {
+        sign = -sign;
+        filt = (2. * sign) / (k * k);
+        arg = ORC_PI * k / (2. * (half + 2));
+        if (family == 0)
+            wind = pow((alpha1 + alpha2 * cos(arg) * cos(arg)), h_beta);
+        else
+            wind = powf(alpha1 + alpha2 * cosf(arg) * cosf(arg), h_beta);
+        coef[half + k] = filt * wind;
+        central = central + coef[half + k];
+        coef[half - k] = coef[half + k];
+    }
+    coef[half] = -2. * central;
+}
+
+/* central second-derivative weights, order+1 floats.
+ * functions.c:78-123 == fd.c:54-97. */
+void orc_calc_coefs(int order, int family, float *coef)
+{
+    static const double t2[] = {1., -2., 1.};
+    static const double t4[] = {-1. / 12., 4. / 3., -5. / 2., 4. / 3., -1. / 12.};
+    static const double t6[] = {1. / 90., -3. / 20., 3. / 2., -49. / 18., 3. / 2., -3. / 20., 1. / 90.};
+    static const double t8[] = {-1. / 560., 8. / 315., -1. / 5., 8. / 5., -205. / 72.,
+                                8. / 5., -1. / 5., 8. / 315., -1. / 560.};
+    const double *t = NULL;
+    memset(coef, 0, (size_t)(order + 1) * sizeof(float));
+    if (order == 2) t = t2;
+    else if (order == 4) t = t4;
+    else if (order == 6) t = t6;
+    else if (order == 8) t = t8;
+    if (t) {
+        for (int k = 0; k <= order; k++) coef[k] = (float)t[k];
+    } else {
+        orc_makeo2(coef, order, family);
+    }
+}
+
+/* 1/dx^2, 1/dz^2, dt^2 exactly as fd-code.cu:203-205 == fd.c:12-14:
+ * the reciprocals are formed in double and stored to float. */
+void orc_scalars(float dx, float dz, float dt, float *dx2inv, float *dz2inv, float *dt2)
+{
+    *dx2inv = (1. / dx) * (1. / dx);
+    *dz2inv = (1. / dz) * (1. / dz);
+    *dt2 = dt * dt;
+}
+
+/* premultiplied weights of the GPU family, fd-code.cu:214-217. */
+void orc_premult_coefs(int order, float dx, float dz, float *cx, float *cz)
+{
+    float c[64], dx2inv, dz2inv, dt2;
+    orc_calc_coefs(order, 0, c);
+    orc_scalars(dx, dz, 1.0f, &dx2inv, &dz2inv, &dt2);
+    for (int k = 0; k <= order; k++) {
+        cz[k] = dz2inv * c[k];
+        cx[k] = dx2inv * c[k];
+    }
+}
+
+/* Ricker wavelet.
+ * family 0: functions.c:267-299 (C: exp in double, no cut-off).
+ * family 1: ptsrc.c:60-99 (built as C++: expf; samples with it*dt > 2/fpeak
+ *           are zero). */
+static float orc_ricker(float t, float fpeak, int family)
+{
+    float x, xx;
+    x = ORC_PI * fpeak * t;
+    xx = x * x;
+    if (family == 0) return exp(-xx) * (1.0 - 2.0 * xx);
+    return expf(-xx) * (1.0 - 2.0 * xx);
+}
+
+void orc_ricker_wavelet(int nt, float dt, float fpeak, int family, float *s)
+{
+    for (int it = 0; it < nt; it++) {
+        if (family == 1 && it * dt > 2.0 / fpeak)
+            s[it] = 0.0;
+        else
+            s[it] = orc_ricker(it * dt - 1.0 / fpeak, fpeak, family);
+    }
+}
+
+/* Gaussian sponge table, nb floats.
+ * family 0: fd-code.cu:159-166.  That file is C++ (nvcc host pass), so
+ *           log/sqrt of a float pick the float overloads; pow(float,int)
+ *           promotes to double.
+ * family 1: taper.c:33-42 (F used directly, no dfrac).
+ * family 2: functions.c:361-379 (C: log/sqrt in double) -- table computed by
+ *           the reference's taper_init but never used by its kernels.    */
+void orc_taper_table(int nb, float fac, int family, float *tab)
+{
+    float dfrac;
+    if (family == 0)
+        dfrac = sqrtf(-logf(fac)) / (1. * nb);
+    else if (family == 2)
+        dfrac = sqrt(-log(fac)) / (1. * nb);
+    else
+        dfrac = fac;
+    for (int i = 0; i < nb; i++) {
+        double a = (double)(dfrac * (nb - i));
+        tab[i] = exp(-(a * a));
+    }
+}
+
+/* constant extension of a squared-velocity (or velocity) field, taper.c:7-23 */
+void orc_extendvel(int nx, int nz, int nxb, int nzb, float *vel)
+{
+    int nze = nz + 2 * nzb, nxe = nx + 2 * nxb;
+    for (int ix = nxb; ix < nxb + nx; ix++) {
+        float *row = vel + (size_t)ix * nze;
+        for (int iz = 0; iz < nzb; iz++) row[iz] = row[nzb];
+        for (int iz = nzb + nz; iz < nze; iz++) row[iz] = row[nz + nzb - 1];
+    }
+    for (int iz = 0; iz < nze; iz++) {
+        for (int ix = 0; ix < nxb; ix++) vel[(size_t)ix * nze + iz] = vel[(size_t)nxb * nze + iz];
+        for (int ix = nxb + nx; ix < nxe; ix++)
+            vel[(size_t)ix * nze + iz] = vel[(size_t)(nx + nxb - 1) * nze + iz];
+    }
+}
+
+/* one random-boundary sample, functions.c:314,323,328,345-346,355-356:
+ * integer draw in a window of width 2*delta+ (v - v_ave) around v_ave. */
+static float orc_rnd_draw(float v, float v_ave, float delta)
+{
+    return rand() % (int)(v + delta - (v_ave - delta) + 1) + v_ave - delta;
+}
+
+/* "hybrid" random boundary of the GPU family, functions.c:301-359.
+ * Uses libc rand() exactly like the reference (unseeded there; callers of the
+ * oracle decide about srand).  vel is the extended [nxe][nze] velocity. */
+void orc_extendvel_linear(int nx, int nz, int nxb, int nzb, float *vel)
+{
+    const float l_lim = 300., delta = 200.;
+    int nze = nz + 2 * nzb;
+    float v, v_ave;
+#define V(ix, iz) vel[(size_t)(ix) * nze + (iz)]
+    for (int ix = 0; ix < nx; ix++) {
+        for (int iz = 0; iz < nzb; iz++) {
+            V(ix + nxb, iz) = V(ix + nxb, nzb); /* top: constant */
+            v = V(ix + nxb, nzb + nz - 1);      /* bottom: random */
+            v_ave = v - (v - l_lim) * (iz) / (nzb - 1);
+            V(ix + nxb, nz + nzb + iz) = orc_rnd_draw(v, v_ave, delta);
+        }
+    }
+    for (int iz = 0; iz < nz; iz++) {
+        for (int ix = 0; ix < nxb; ix++) {
+            v = V(nxb, nzb + iz); /* left */
+            v_ave = v - (v - l_lim) * (ix) / (nxb - 1);
+            V(nxb - 1 - ix, nzb + iz) = orc_rnd_draw(v, v_ave, delta);
+            v = V(nxb + nx - 1, nzb + iz); /* right */
+            v_ave = v - (v - l_lim) * (ix) / (nxb - 1);
+            V(nxb + nx + ix, nzb + iz) = orc_rnd_draw(v, v_ave, delta);
+        }
+    }
+    for (int iz = 0; iz < nzb; iz++) { /* top corners: constant */
+        for (int ix = 0; ix < nxb; ix++) {
+            V(ix, iz) = V(nxb, iz);
+            V(nxb + nx + ix, iz) = V(nxb + nx - 1, iz);
+        }
+    }
+    for (int iz = 0; iz < nzb; iz++) { /* bottom-left corner */
+        for (int ix = 0; ix <= iz; ix++) {
+            v = V(nxb, nzb + nz - 1);
+            v_ave = v - (v - l_lim) * (nxb - 1 - ix) / (nzb - 1);
+            V(ix, nz + 2 * nzb - 1 - iz) = orc_rnd_draw(v, v_ave, delta);
+            V(iz, nz + 2 * nzb - 1 - ix) = orc_rnd_draw(v, v_ave, delta);
+        }
+    }
+    for (int iz = 0; iz < nzb; iz++) { /* bottom-right corner */
+        for (int ix = 0; ix <= iz; ix++) {
+            v = V(nxb + nx - 1, nzb + nz - 1);
+            v_ave = v - (v - l_lim) * (nxb - 1 - ix) / (nzb - 1);
+            V(nx + 2 * nxb - 1 - ix, nz + 2 * nzb - 1 - iz) = orc_rnd_draw(v, v_ave, delta);
+            V(nx + 2 * nxb - 1 - iz, nz + 2 * nzb - 1 - ix) = orc_rnd_draw(v, v_ave, delta);
+        }
+    }
+#undef V
+}
+
+void orc_srand(unsigned seed) { srand(seed); }
+
+/* ------------------------------------------------------------------ */
+/* Kernels                                                              */
+/* ------------------------------------------------------------------ */
+
+/* Recipe G Laplacian (kernel_lap, fd-code.cu:53-78 ==
+ * fd-source-code.cu:110-135 == fd-source-code.dp.cpp:112-142):
+ * two float accumulators, taps in ascending io, summed at the end; no FMA.
+ * Written for h <= i < ilim, h <= j < jlim; everything else is untouched
+ * (callers keep the ring at 0: quirk Q2). */
+void orc_lap_G(int order, int nxe, int nze, int ilim, int jlim, const float *p, float *lap,
+               const float *cx, const float *cz)
+{
+    int h = order / 2;
+    if (ilim > nxe - h) ilim = nxe - h;
+    if (jlim > nze - h) jlim = nze - h;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int i = h; i < ilim; i++) {
+        for (int j = h; j < jlim; j++) {
+            float acmx = 0, acmz = 0;
+            for (int io = 0; io <= order; io++) {
+                int a = io - h;
+                acmz += p[(size_t)i * nze + j + a] * cz[io];
+                acmx += p[(size_t)(i + a) * nze + j] * cx[io];
+            }
+            lap[(size_t)i * nze + j] = acmz + acmx;
+        }
+    }
+}
+
+/* Recipe C Laplacian (fd_step first loop nest, fd.c:28-37): one accumulator,
+ * z tap then x tap per io, each tap (p*coef)*d2inv. */
+void orc_lap_C(int order, int nxe, int nze, const float *p, float *lap, const float *coefs,
+               float dx2inv, float dz2inv)
+{
+    int h = order / 2;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int i = h; i < nxe - h; i++) {
+        for (int j = h; j < nze - h; j++) {
+            float acm = 0;
+            for (int io = 0; io <= order; io++) {
+                acm += p[(size_t)i * nze + j + io - h] * coefs[io] * dz2inv;
+                acm += p[(size_t)(i + io - h) * nze + j] * coefs[io] * dx2inv;
+            }
+            lap[(size_t)i * nze + j] = acm;
+        }
+    }
+}
+
+/* leapfrog update (kernel_time fd-code.cu:80-92 == fd.c:39-43): the literal
+ * "2." is a double, so the two adds happen in FP64 with one rounding to
+ * float; v2*dt2*lap is two float multiplies. Covers i < ux, j < uz. */
+void orc_time(int nxe, int nze, int ux, int uz, const float *p, float *pp, const float *v2,
+              const float *lap, float dt2)
+{
+    (void)nxe;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int i = 0; i < ux; i++) {
+        for (int j = 0; j < uz; j++) {
+            size_t k = (size_t)i * nze + j;
+            pp[k] = 2. * p[k] - pp[k] + v2[k] * dt2 * lap[k];
+        }
+    }
+}
+
+/* top-only sponge (kernel_tapper fd-code.cu:94-117 == taper_apply2
+ * taper.c:69-84).  z factor for j < uzb on rows i < ux; then the x factor on
+ * the two top corners (rows i and nxe-1-i, i < nxb).  The reference GPU
+ * kernel races on the mirrored rows (quirk Q4); effective semantics = both
+ * factors applied, z first, which is also exactly taper_apply2. */
+void orc_taper_top(float *a, int nxe, int nze, int nxb, int ux, int uzb, const float *taperx,
+                   const float *taperz)
+{
+    for (int i = 0; i < ux; i++)
+        for (int j = 0; j < uzb; j++) a[(size_t)i * nze + j] *= taperz[j];
+    for (int i = 0; i < nxb; i++) {
+        for (int j = 0; j < uzb; j++) {
+            a[(size_t)i * nze + j] *= taperx[i];
+            a[(size_t)(nxe - 1 - i) * nze + j] *= taperx[i];
+        }
+    }
+}
+
+/* four-sided sponge (taper_apply, taper.c:47-67). */
+void orc_taper_4(float *a, int nx, int nz, int nxb, int nzb, const float *taperx,
+                 const float *taperz)
+{
+    int nze = nz + 2 * nzb, nxe = nx + 2 * nxb;
+    for (int i = 0; i < nxe; i++) {
+        float *row = a + (size_t)i * nze;
+        for (int j = 0; j < nzb; j++) row[j] *= taperz[j];
+        for (int j = nzb - 1, k = 0; j > -1; j--, k++) row[nz + nzb + k] *= taperz[j];
+    }
+    for (int j = 0; j < nze; j++) {
+        for (int i = 0; i < nxb; i++) a[(size_t)i * nze + j] *= taperx[i];
+        for (int i = nxb - 1, k = 0; i > -1; i--, k++) a[(size_t)(nx + nxb + k) * nze + j] *= taperx[i];
+    }
+}
+
+/* 7x7 Gaussian point source (ptsrc, ptsrc.c:12-58; built as C++ => expf). */
+void orc_ptsrc(int xs, int zs, int nxe, int nze, float ts, float *s)
+{
+    int x0 = xs - 3 < 0 ? 0 : xs - 3, x1 = xs + 3 > nxe - 1 ? nxe - 1 : xs + 3;
+    int z0 = zs - 3 < 0 ? 0 : zs - 3, z1 = zs + 3 > nze - 1 ? nze - 1 : zs + 3;
+    float xsn = xs, zsn = zs;
+    for (int ix = x0; ix <= x1; ix++) {
+        for (int iz = z0; iz <= z1; iz++) {
+            float xn = ix - xsn, zn = iz - zsn;
+            s[(size_t)ix * nze + iz] += ts * expf(-xn * xn - zn * zn);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Config 1: the stencil program (fd-source-code.cu:277-352;            */
+/* fd-source-code.dp.cpp:226-272): one Laplacian sweep, ring = 0.       */
+/* ------------------------------------------------------------------ */
+void orc_stencil(int order, int nxe, int nze, float dx, float dz, const float *in, float *out)
+{
+    float cx[64], cz[64];
+    orc_premult_coefs(order, dx, dz, cx, cz);
+    memset(out, 0, (size_t)nxe * nze * sizeof(float));
+    orc_lap_G(order, nxe, nze, nxe, nze, in, out, cx, cz);
+}
+
+/* ------------------------------------------------------------------ */
+/* GPU family pipelines                                                 */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    int order, nxe, nze, nxb, nzb, nt;
+    float dx, dz, dt, fac;
+    int compat; /* 1: truncated launch extents of the reference (quirk Q1) */
+} orc_gpu_cfg;
+
+static void gpu_extents(const orc_gpu_cfg *c, int *ux, int *uz, int *uzb, int *ilim, int *jlim)
+{
+    int h = c->order / 2;
+    if (c->compat) {
+        /* fd-code.cu:185-195: div_x is an int, so ceil() sees a truncated value */
+        *ux = (c->nxe / ORC_SIZEBLOCK) * ORC_SIZEBLOCK;
+        *uz = (c->nze / ORC_SIZEBLOCK) * ORC_SIZEBLOCK;
+        *uzb = (c->nzb / ORC_SIZEBLOCK) * ORC_SIZEBLOCK;
+        *ilim = h + *ux;
+        *jlim = h + *uz;
+    } else {
+        *ux = c->nxe;
+        *uz = c->nze;
+        *uzb = c->nzb;
+        *ilim = c->nxe;
+        *jlim = c->nze;
+    }
+}
+
+/* fd_forward, fd-code.cu:247-288.  p, pp: [nxe][nze] in/out (the reference
+ * passes zeros in and reads both levels back).  On return p = older level
+ * (tapered once in the last iteration), pp = newest level.  Because the
+ * reference swaps device pointers an odd/even number of times but copies
+ * d_p -> p, d_pp -> pp at the end, the host arrays come back in role order. */
+void orc_gpu_forward(const orc_gpu_cfg *c, float *p, float *pp, const float *v2, const float *srce,
+                     int sx, int sz)
+{
+    size_t n = (size_t)c->nxe * c->nze;
+    int ux, uz, uzb, ilim, jlim;
+    float cx[64], cz[64], dx2inv, dz2inv, dt2;
+    float *tx = (float *)malloc(sizeof(float) * (c->nxb + 1));
+    float *tz = (float *)malloc(sizeof(float) * (c->nzb + 1));
+    float *lap = (float *)calloc(n, sizeof(float));
+    float *a = (float *)malloc(n * sizeof(float)), *b = (float *)malloc(n * sizeof(float)), *t;
+    gpu_extents(c, &ux, &uz, &uzb, &ilim, &jlim);
+    orc_premult_coefs(c->order, c->dx, c->dz, cx, cz);
+    orc_scalars(c->dx, c->dz, c->dt, &dx2inv, &dz2inv, &dt2);
+    orc_taper_table(c->nxb, c->fac, 0, tx);
+    orc_taper_table(c->nzb, c->fac, 0, tz);
+    memcpy(a, p, n * sizeof(float));  /* d_p  */
+    memcpy(b, pp, n * sizeof(float)); /* d_pp */
+    for (int it = 0; it < c->nt; it++) {
+        t = b; b = a; a = t; /* fd-code.cu:260-262 */
+        orc_taper_top(a, c->nxe, c->nze, c->nxb, ux, uzb, tx, tz);
+        orc_taper_top(b, c->nxe, c->nze, c->nxb, ux, uzb, tx, tz);
+        orc_lap_G(c->order, c->nxe, c->nze, ilim, jlim, a, lap, cx, cz);
+        orc_time(c->nxe, c->nze, ux, uz, a, b, v2, lap, dt2);
+        b[(size_t)sx * c->nze + sz] += srce[it]; /* kernel_src: effective +1x (Q3) */
+    }
+    memcpy(p, a, n * sizeof(float));
+    memcpy(pp, b, n * sizeof(float));
+    free(tx); free(tz); free(lap); free(a); free(b);
+}
+
+/* fd_back, fd-code.cu:290-341.  snap0 = P, snap1 = PP from fd_forward
+ * (main(), fd-code.cu:502-507).  dobs: this shot's traces [nx][nt].
+ * imloc [nx][nz] accumulates (caller zeroes it, fd-code.cu:515). */
+void orc_gpu_back(const orc_gpu_cfg *c, const float *snap0, const float *snap1, const float *v2,
+                  const float *dobs, int gz, float *imloc)
+{
+    size_t n = (size_t)c->nxe * c->nze;
+    int nx = c->nxe - 2 * c->nxb, nz = c->nze - 2 * c->nzb, nt = c->nt;
+    int ux, uz, uzb, ilim, jlim;
+    float cx[64], cz[64], dx2inv, dz2inv, dt2;
+    float *tx = (float *)malloc(sizeof(float) * (c->nxb + 1));
+    float *tz = (float *)malloc(sizeof(float) * (c->nzb + 1));
+    float *lap = (float *)calloc(n, sizeof(float));
+    float *a = (float *)calloc(n, sizeof(float)), *b = (float *)calloc(n, sizeof(float));
+    float *ar = (float *)calloc(n, sizeof(float)), *br = (float *)calloc(n, sizeof(float)), *t;
+    gpu_extents(c, &ux, &uz, &uzb, &ilim, &jlim);
+    orc_premult_coefs(c->order, c->dx, c->dz, cx, cz);
+    orc_scalars(c->dx, c->dz, c->dt, &dx2inv, &dz2inv, &dt2);
+    orc_taper_table(c->nxb, c->fac, 0, tx);
+    orc_taper_table(c->nzb, c->fac, 0, tz);
+    for (int it = 0; it < nt; it++) {
+        if (it == 0 || it == 1) { /* fd-code.cu:304-314: load the two saved levels */
+            memcpy(b, it == 0 ? snap1 : snap0, n * sizeof(float));
+        } else { /* time-reversed reconstruction: same update, no sponge, no source */
+            orc_lap_G(c->order, c->nxe, c->nze, ilim, jlim, a, lap, cx, cz);
+            orc_time(c->nxe, c->nze, ux, uz, a, b, v2, lap, dt2);
+        }
+        t = b; b = a; a = t;
+        /* receiver wavefield */
+        orc_taper_top(ar, c->nxe, c->nze, c->nxb, ux, uzb, tx, tz);
+        orc_taper_top(br, c->nxe, c->nze, c->nxb, ux, uzb, tx, tz);
+        orc_lap_G(c->order, c->nxe, c->nze, ilim, jlim, ar, lap, cx, cz);
+        orc_time(c->nxe, c->nze, ux, uz, ar, br, v2, lap, dt2);
+        for (int i = 0; i < nx && i < ux; i++) /* kernel_sism, effective +1x (Q3) */
+            br[(size_t)(i + c->nxb) * c->nze + gz] += dobs[(size_t)i * nt + (nt - 1 - it)];
+        for (int i = 0; i < nx && i < ux; i++) /* kernel_img */
+            for (int j = 0; j < nz && j < uz; j++)
+                imloc[(size_t)i * nz + j] +=
+                    a[(size_t)(i + c->nxb) * c->nze + (j + c->nzb)] * br[(size_t)(i + c->nxb) * c->nze + (j + c->nzb)];
+        t = br; br = ar; ar = t;
+    }
+    free(tx); free(tz); free(lap); free(a); free(b); free(ar); free(br);
+}
+
+/* ------------------------------------------------------------------ */
+/* CPU family pipelines                                                 */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    int order, nx, nz, nxb, nzb, nt;
+    float dx, dz, dt, fac;
+} orc_cpu_cfg;
+
+/* fd_step, fd.c:24-46.  lap is the persistent scratch array whose ring stays
+ * zero (memset in fd_init, fd.c:19). */
+void orc_fd_step(int order, int nxe, int nze, const float *p, float *pp, const float *v2,
+                 float *lap, float dx, float dz, float dt)
+{
+    float coefs[64], dx2inv, dz2inv, dt2;
+    orc_calc_coefs(order, 1, coefs);
+    orc_scalars(dx, dz, dt, &dx2inv, &dz2inv, &dt2);
+    orc_lap_C(order, nxe, nze, p, lap, coefs, dx2inv, dz2inv);
+    orc_time(nxe, nze, nxe, nze, p, pp, v2, lap, dt2);
+}
+
+/* mod_main time loop for one shot, mod_main.cpp:141-169.
+ * v2: extended squared velocity.  data: [nx][nt] seismogram of this shot. */
+void orc_mod_shot(const orc_cpu_cfg *c, const float *v2, const float *srce, int sx, int sz, int gz,
+                  float *data)
+{
+    int nxe = c->nx + 2 * c->nxb, nze = c->nz + 2 * c->nzb, nt = c->nt;
+    size_t n = (size_t)nxe * nze;
+    float *tx = (float *)malloc(sizeof(float) * (c->nxb + 1));
+    float *tz = (float *)malloc(sizeof(float) * (c->nzb + 1));
+    float *lap = (float *)calloc(n, sizeof(float));
+    float *P = (float *)calloc(n, sizeof(float)), *PP = (float *)calloc(n, sizeof(float)), *t;
+    orc_taper_table(c->nxb, c->fac, 1, tx);
+    orc_taper_table(c->nzb, c->fac, 1, tz);
+    for (int it = 0; it < nt; it++) {
+        orc_fd_step(c->order, nxe, nze, P, PP, v2, lap, c->dx, c->dz, c->dt);
+        orc_ptsrc(sx, sz, nxe, nze, srce[it], PP);
+        orc_taper_4(PP, c->nx, c->nz, c->nxb, c->nzb, tx, tz);
+        orc_taper_4(P, c->nx, c->nz, c->nxb, c->nzb, tx, tz);
+        for (int ix = 0; ix < c->nx; ix++) data[(size_t)ix * nt + it] = P[(size_t)(ix + c->nxb) * nze + gz];
+        t = PP; PP = P; P = t;
+    }
+    free(tx); free(tz); free(lap); free(P); free(PP);
+}
+
+/* rtm_main, one shot, rtm_main.cpp:158-240.
+ * dobs_all: the whole [ns][nx][nt] block; the back-injection index nt-it and
+ * x offset nzb are the reference's (quirk Q5): at it=0 it reads the first
+ * sample of the next trace; one float past the block reads 0 (the reference
+ * reads whatever follows its heap block -- zero for the mmap'ed sizes used).
+ * imloc [nx][nz] is overwritten.  swf_out (optional, nt*nx*nz) returns the
+ * stored forward history for tests. */
+void orc_rtm_shot(const orc_cpu_cfg *c, const float *v2, const float *srce, int sx, int sz, int gz,
+                  const float *dobs_all, int ns, int is, float *imloc, float *swf_out)
+{
+    int nx = c->nx, nz = c->nz, nt = c->nt;
+    int nxe = nx + 2 * c->nxb, nze = nz + 2 * c->nzb;
+    size_t n = (size_t)nxe * nze, ni = (size_t)nx * nz, ntot = (size_t)ns * nx * nt;
+    float *tx = (float *)malloc(sizeof(float) * (c->nxb + 1));
+    float *tz = (float *)malloc(sizeof(float) * (c->nzb + 1));
+    float *lap = (float *)calloc(n, sizeof(float));
+    float *P = (float *)calloc(n, sizeof(float)), *PP = (float *)calloc(n, sizeof(float)), *t;
+    float *swf = swf_out ? swf_out : (float *)malloc(ni * nt * sizeof(float));
+    float *rwf = (float *)malloc(ni * nt * sizeof(float));
+    orc_taper_table(c->nxb, c->fac, 1, tx);
+    orc_taper_table(c->nzb, c->fac, 1, tz);
+    for (int it = 0; it < nt; it++) { /* forward, rtm_main.cpp:166-188 */
+        orc_fd_step(c->order, nxe, nze, P, PP, v2, lap, c->dx, c->dz, c->dt);
+        PP[(size_t)sx * nze + sz] += srce[it];
+        orc_taper_top(PP, nxe, nze, c->nxb, nxe, c->nzb, tx, tz);
+        orc_taper_top(P, nxe, nze, c->nxb, nxe, c->nzb, tx, tz);
+        for (int ix = 0; ix < nx; ix++)
+            memcpy(swf + (size_t)it * ni + (size_t)ix * nz, P + (size_t)(ix + c->nxb) * nze + c->nzb,
+                   nz * sizeof(float));
+        t = PP; PP = P; P = t;
+    }
+    memset(P, 0, n * sizeof(float));
+    memset(PP, 0, n * sizeof(float));
+    memset(imloc, 0, ni * sizeof(float));
+    for (int it = 0; it < nt; it++) { /* backward, rtm_main.cpp:196-220 */
+        orc_fd_step(c->order, nxe, nze, P, PP, v2, lap, c->dx, c->dz, c->dt);
+        for (int ix = 0; ix < nx; ix++) {
+            size_t k = ((size_t)is * nx + ix) * nt + (nt - it);
+            PP[(size_t)(ix + c->nzb) * nze + gz] += (k < ntot) ? dobs_all[k] : 0.0f;
+        }
+        orc_taper_top(PP, nxe, nze, c->nxb, nxe, c->nzb, tx, tz);
+        orc_taper_top(P, nxe, nze, c->nxb, nxe, c->nzb, tx, tz);
+        for (int ix = 0; ix < nx; ix++)
+            memcpy(rwf + (size_t)it * ni + (size_t)ix * nz, P + (size_t)(ix + c->nxb) * nze + c->nzb,
+                   nz * sizeof(float));
+        t = PP; PP = P; P = t;
+    }
+    for (int it = 0; it < nt; it++) /* imaging, rtm_main.cpp:223-229 */
+        for (size_t k = 0; k < ni; k++) imloc[k] += swf[(size_t)(nt - it - 1) * ni + k] * rwf[(size_t)it * ni + k];
+    free(tx); free(tz); free(lap); free(P); free(PP); free(rwf);
+    if (!swf_out) free(swf);
+}
