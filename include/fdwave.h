@@ -1,0 +1,186 @@
+/*
+ * fdwave.h -- C ABI of the B200-native finite-difference acoustic propagation
+ * library (libfdwave.so).  Plain C: pointers, sizes and ints only.
+ *
+ * The reference (FernandoSchett/parallel_finite_difference_computation) has no
+ * plugin or FFI boundary: its hot path is a handful of C functions called by
+ * each program's main().  Every entry point below names the reference
+ * function(s) it replaces.  Shims with the reference's exact signatures live
+ * in fdwave_cpufam.h / fdwave_gpufam.h (two libraries, because both families
+ * export an `fd_init` with different argument lists).
+ *
+ * Conventions
+ *   - all arrays are float32, logical shape [nxe][nze], z fastest, exactly the
+ *     reference's alloc2float(nze,nxe) block (functions.c:168-182);
+ *     nxe = nx + 2*nxb, nze = nz + 2*nzb (fd-code.cu:410-411);
+ *   - "newest"/"older" name the two time levels explicitly (the reference's
+ *     P/PP naming differs between its two families);
+ *   - every function returns FDW_OK (0) or a negative error code;
+ *     fdw_last_error() gives the message.  No function falls back to the CPU:
+ *     without a CUDA device the compute entry points fail with FDW_ERR_CUDA.
+ *   - a context is bound to one device and one stream; calls on it are
+ *     asynchronous up to the next download/sync.
+ */
+#ifndef FDWAVE_H
+#define FDWAVE_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDW_OK 0
+#define FDW_ERR_ARG (-1)
+#define FDW_ERR_CUDA (-2)
+#define FDW_ERR_NOMEM (-3)
+#define FDW_ERR_IO (-4)
+#define FDW_ERR_STATE (-5)
+#define FDW_ERR_UNSUPPORTED (-6)
+
+/* table family: which of the reference's two code families a host table or a
+ * context reproduces */
+#define FDW_FAMILY_GPU 0 /* cuda_reference_RTM / dpct_migrated_* */
+#define FDW_FAMILY_CPU 1 /* dpct_gpu_rtm_domain_division */
+
+/* arithmetic recipe of the Laplacian + update */
+#define FDW_RECIPE_G 0    /* kernel_lap + kernel_time, fd-code.cu:53-92 (bit-exact) */
+#define FDW_RECIPE_C 1    /* fd_step, fd.c:24-46 (bit-exact) */
+#define FDW_RECIPE_FAST 2 /* symmetric pairs + FMA, float update (tolerance-checked) */
+
+/* sponge geometry */
+#define FDW_TAPER_NONE 0
+#define FDW_TAPER_TOP 1  /* kernel_tapper fd-code.cu:94-117 == taper_apply2 taper.c:69-84 */
+#define FDW_TAPER_FOUR 2 /* taper_apply taper.c:47-67 */
+
+/* source kind */
+#define FDW_SRC_POINT 0  /* kernel_src fd-code.cu:119-122, rtm_main.cpp:171 */
+#define FDW_SRC_GAUSS7 1 /* ptsrc ptsrc.c:12-58 */
+
+typedef struct fdw_ctx fdw_ctx;
+
+typedef struct fdw_params {
+    int nx, nz;   /* interior grid */
+    int nxb, nzb; /* sponge / border widths */
+    int order;    /* 2, 4, 6 or 8 */
+    float dx, dz, dt;
+    float fac;          /* sponge factor (meaning differs per family, see fdw_taper_table) */
+    int family;         /* FDW_FAMILY_*: tables + step ordering */
+    int recipe;         /* FDW_RECIPE_* */
+    int taper;          /* FDW_TAPER_* */
+    int compat_extents; /* 1: reproduce the reference GPU family's truncated launch
+                           extents floor(n/8)*8 (fd-code.cu:185-195) */
+    int device;         /* CUDA device ordinal */
+    int slab_x0, slab_x1; /* extended-grid rows owned by this context; 0,0 = all rows */
+    int history;        /* 1: allocate the forward history needed by fdw_rtm_shot_cpu */
+    int nt;             /* time steps per shot (sizes wavelet, traces, history) */
+} fdw_params;
+
+/* ---------------------------------------------------------------- host tables
+ * Pure host code, callable without a GPU. */
+
+/* calc_coefs: functions.c:78-123 (family GPU), fd.c:54-97 (family CPU). order+1 floats. */
+int fdw_calc_coefs(int order, int family, float *coefs);
+/* ricker_wavelet: functions.c:293-299 (GPU), ptsrc.c:88-99 (CPU: zero after 2/fpeak). */
+int fdw_ricker_wavelet(int nt, float dt, float fpeak, int family, float *s);
+/* sponge table: fd-code.cu:159-166 (GPU: fac -> dfrac), taper.c:33-42 (CPU: fac used directly). */
+int fdw_taper_table(int nb, float fac, int family, float *tab);
+/* extendvel, taper.c:7-23: constant extension of an [nxe][nze] array in place. */
+int fdw_extendvel(int nx, int nz, int nxb, int nzb, float *vel);
+/* extendvel_linear, functions.c:301-359: random "hybrid" border, libc rand(). */
+int fdw_extendvel_linear(int nx, int nz, int nxb, int nzb, float *vel);
+/* 7x7 Gaussian weights of ptsrc (ptsrc.c:51-56), row = x offset -3..3. */
+int fdw_ptsrc_weights(float *w49);
+
+/* input.dat, both dialects.  All reference keys; absent ints are -1, absent
+ * floats -1.0, absent strings empty (then defaults as fd-code.cu:367-377 /
+ * mod_main.cpp:76-85 are applied when apply_defaults != 0). */
+typedef struct fdw_input {
+    char tmpdir[512], vpfile[512], datfile[512], vel_ext_file[512];
+    int nz, nx, nt, ns, sz, fsx, ds, gz, order, nzb, nxb, iss, rnd;
+    float dz, dx, dt, fpeak, fac;
+    int has_datfile, has_vel_ext_file;
+} fdw_input;
+/* GPU-family dialect: first line containing the key as a substring wins
+ * (functions.c:10-75). */
+int fdw_read_input_gpu(const char *path, int apply_defaults, fdw_input *out);
+/* stencil program dialect (fd-source-code.cu:34-108): tmpdir is the input file. */
+int fdw_read_input_stencil(const char *path, fdw_input *out);
+/* CPU-family dialect: CWP getpar semantics on a par= file -- whitespace
+ * separated name=value tokens, exact name match, last occurrence wins
+ * (lib/cwp/src/par/lib/getpars.c:447-453). */
+int fdw_read_input_cpu(const char *path, int apply_defaults, fdw_input *out);
+
+/* ---------------------------------------------------------------- context */
+const char *fdw_last_error(void);
+int fdw_device_count(void);
+int fdw_create(const fdw_params *prm, fdw_ctx **out);
+void fdw_destroy(fdw_ctx *ctx);
+/* run on an existing cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int fdw_set_stream(fdw_ctx *ctx, void *cuda_stream);
+int fdw_sync(fdw_ctx *ctx);
+/* squared velocity of the whole extended grid, host [nxe][nze] (vel2 of
+ * fd-code.cu:490-494 / mod_main.cpp:120-126).  The slab's rows are taken. */
+int fdw_set_v2(fdw_ctx *ctx, const float *v2);
+/* source wavelet srce[nt] (fd-code.cu:402-403) */
+int fdw_set_wavelet(fdw_ctx *ctx, const float *srce, int nt);
+/* source position in extended-grid indices (sx[is], sz after "+= nzb") */
+int fdw_set_source(fdw_ctx *ctx, int sx, int sz, int kind);
+/* the two time levels of pair 0 (source field) or 1 (receiver field) */
+int fdw_fields_zero(fdw_ctx *ctx, int pair);
+int fdw_fields_upload(fdw_ctx *ctx, int pair, const float *newest, const float *older);
+int fdw_fields_download(fdw_ctx *ctx, int pair, float *newest, float *older);
+/* nsteps time levels of pair 0 starting at step index it0, with the context's
+ * sponge and source: the loop body of fd_forward (fd-code.cu:259-284) for
+ * family GPU, of rtm_main's forward loop (rtm_main.cpp:166-188) for family
+ * CPU with FDW_SRC_POINT, of mod_main's (mod_main.cpp:146-168) with
+ * FDW_SRC_GAUSS7 + FDW_TAPER_FOUR.  Asynchronous. */
+int fdw_advance(fdw_ctx *ctx, int it0, int nsteps);
+
+/* upload the two levels from host memory, run nsteps levels from step index
+ * it0, download both levels back into the same host arrays: the body of
+ * fd_forward (fd-code.cu:257-286) for arbitrary initial fields.  Synchronous. */
+int fdw_propagate(fdw_ctx *ctx, float *newest, float *older, int it0, int nsteps);
+
+/* ---------------------------------------------------------------- pipelines */
+/* fd_forward (fd-code.cu:247-288): zero fields, nt steps, returns the two last
+ * levels (P = older, PP = newest; either may be NULL to leave them on the
+ * device for fdw_backward). */
+int fdw_forward(fdw_ctx *ctx, int sx, int sz, float *P, float *PP);
+/* fd_back (fd-code.cu:290-341): P/PP = the two saved levels (NULL,NULL = use
+ * the ones fdw_forward left on the device), dobs = this shot's traces
+ * [nx][nt], imloc [nx][nz] receives the shot image. */
+int fdw_backward(fdw_ctx *ctx, const float *P, const float *PP, const float *dobs, int gz, float *imloc);
+/* one shot of mod_main (mod_main.cpp:141-169): data [nx][nt]. */
+int fdw_model_shot(fdw_ctx *ctx, int sx, int sz, int gz, float *data);
+/* one shot of rtm_main (rtm_main.cpp:158-240): dobs_all = the whole
+ * [ns][nx][nt] block (the reference's index quirk Q5 reaches into the next
+ * trace), imloc [nx][nz].  Needs params.history = 1. */
+int fdw_rtm_shot_cpu(fdw_ctx *ctx, int sx, int sz, int gz, const float *dobs_all, int ns, int is,
+                     float *imloc);
+/* the stencil program (fd-source-code.cu:277-352): one Laplacian sweep of an
+ * [nxe][nze] host array, ring of width order/2 = 0. */
+int fdw_stencil(int order, int nxe, int nze, float dx, float dz, const float *in, float *out, int device);
+
+/* ---------------------------------------------------------------- device-resident access
+ * (benchmarks / multi-GPU plumbing; pointers are CUDA device pointers) */
+typedef struct fdw_devinfo {
+    void *newest, *older; /* local row 0, column 0 of pair 0 */
+    void *vdt;
+    long long pitch; /* floats */
+    int nloc, gx0, nxe, nze, guard;
+} fdw_devinfo;
+int fdw_devinfo_get(fdw_ctx *ctx, fdw_devinfo *out);
+/* device time of the work enqueued between mark_begin and mark_end, in ms
+ * (CUDA events on the context's stream) */
+int fdw_mark_begin(fdw_ctx *ctx);
+int fdw_mark_end(fdw_ctx *ctx, float *ms);
+/* number of kernels this context has launched so far */
+long long fdw_launch_count(fdw_ctx *ctx);
+/* standalone Laplacian on device-resident data of pair 0 (newest -> older), for benchmarks */
+int fdw_laplacian_device(fdw_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDWAVE_H */

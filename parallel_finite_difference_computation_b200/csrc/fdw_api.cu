@@ -1,0 +1,827 @@
+/*
+ * fdw_api.cu -- context management and the C ABI of libfdwave (include/fdwave.h).
+ *
+ * Data layout in HBM (per context = per GPU = per slab):
+ *   every wavefield level, the premultiplied velocity fl32(v2*dt2) and the
+ *   image share one pitched layout: row = one x index, `pitch` floats per row
+ *   (multiple of 32 => every row starts on a 128-byte line, float4 columns are
+ *   aligned), nze valid columns followed by >= 4 zero pad columns.  GUARD (4)
+ *   guard rows precede and follow the slab's rows: zeros on a physical grid
+ *   edge, the neighbour's rows (ghost rows) on a slab edge.
+ *   Levels are stored RAW; the sponge multiplications still pending on a level
+ *   are counted in Field::pend and applied on load by the step kernel (see
+ *   fdw_step_core.h) or materialised in place before an export.
+ */
+#ifdef FDW_EMU
+#include "emu_cuda.h" /* tests/emu: host stand-in for the CUDA runtime, unit tests only */
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fdwave.h"
+#include "fdw_internal.h"
+#include "fdw_step_core.h"
+
+using fdw::GUARD;
+using fdw::StepArgs;
+
+/* ------------------------------------------------------------------ errors */
+static thread_local char g_err[512] = "";
+
+extern "C" void fdw_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *fdw_last_error(void) { return g_err; }
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            fdw_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return FDW_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define CHECK(x)               \
+    do {                       \
+        int r_ = (x);          \
+        if (r_ != FDW_OK) return r_; \
+    } while (0)
+
+/* ------------------------------------------------------------------ context */
+struct Field {
+    float *base = nullptr; /* allocation */
+    float *r0 = nullptr;   /* local row 0, column 0 */
+    int pend = 0;          /* sponge multiplications not yet applied to the stored values */
+};
+
+struct fdw_ctx {
+    fdw_params prm;
+    int nxe, nze, gx0, nloc, H;
+    long long pitch;
+    size_t rows_alloc, field_elems;
+    Field f[4];
+    int newest[2], older[2];
+    float *vdt_base = nullptr, *vdt = nullptr;
+    float *tz_base = nullptr, *tz = nullptr, *tx_base = nullptr, *tx = nullptr;
+    float cz[9], cx[9], dz2inv, dx2inv, dt2;
+    int tx_jlim, tz_ilim, tap_jlo, tap_jhi, tap_ilo, tap_ihi;
+    int lap_i0, lap_i1, lap_j0, lap_j1, upd_i1, upd_j1, ncol4;
+    std::vector<float> wavelet;
+    int sx = 0, sz = 0, src_kind = FDW_SRC_POINT;
+    float src_w[49];
+    float *hist = nullptr, *img = nullptr, *dobs_d = nullptr, *rec_d = nullptr;
+    size_t dobs_cap = 0, rec_cap = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long launches = 0;
+    int nsm = 0;
+    bool saved_valid = false;
+    int rows_per_cta_override = 0, threads_override = 0;
+};
+
+static int bind(fdw_ctx *c)
+{
+    CU(cudaSetDevice(c->prm.device));
+    return FDW_OK;
+}
+
+/* ------------------------------------------------------------------ small kernels */
+__global__ void k_scale_rows(float *v, long long n, float s)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = __fmul_rn(v[i], s);
+}
+
+/* apply the sponge cnt times in place (kernel_tapper / taper_apply as a
+ * stand-alone pass; used only to materialise pending factors before export) */
+__global__ void k_materialize(float *r0, long long pitch, int nze, int row_lo, int row_hi, int grow0,
+                              const float *tz, const float *tx, int tx_jlim, int tz_ilim, int cnt)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int lr = row_lo + blockIdx.y;
+    if (j >= nze || lr >= row_hi) return;
+    float v = r0[(long long)lr * pitch + j];
+    const float zf = (grow0 + lr < tz_ilim) ? tz[j] : 1.0f;
+    const float xf = (j < tx_jlim) ? tx[lr] : 1.0f;
+    for (int c = 0; c < cnt; c++) v = __fmul_rn(__fmul_rn(v, zf), xf);
+    r0[(long long)lr * pitch + j] = v;
+}
+
+#ifdef FDW_EMU
+static void thunk_scale_rows(void **a) { k_scale_rows(*(float **)a[0], *(long long *)a[1], *(float *)a[2]); }
+static void thunk_materialize(void **a)
+{
+    k_materialize(*(float **)a[0], *(long long *)a[1], *(int *)a[2], *(int *)a[3], *(int *)a[4], *(int *)a[5],
+                  *(const float **)a[6], *(const float **)a[7], *(int *)a[8], *(int *)a[9], *(int *)a[10]);
+}
+#define FDW_KPTR(kernel, thunk) ((const void *)&thunk)
+#else
+#define FDW_KPTR(kernel, thunk) ((const void *)kernel)
+#endif
+
+/* ------------------------------------------------------------------ helpers */
+static const void *step_kernel(int order, int recipe, int epi)
+{
+    switch (order) {
+    case 2: return fdw_step_kernel_o2(recipe, epi);
+    case 4: return fdw_step_kernel_o4(recipe, epi);
+    case 6: return fdw_step_kernel_o6(recipe, epi);
+    case 8: return fdw_step_kernel_o8(recipe, epi);
+    }
+    return nullptr;
+}
+
+static const void *lap_kernel(int order)
+{
+    switch (order) {
+    case 2: return fdw_lap_kernel_o2();
+    case 4: return fdw_lap_kernel_o4();
+    case 6: return fdw_lap_kernel_o6();
+    case 8: return fdw_lap_kernel_o8();
+    }
+    return nullptr;
+}
+
+static long long pitch_for(int nze) { return ((long long)nze + 4 + 31) / 32 * 32; }
+
+/* launch geometry: one thread per float4 column, CTAs of up to 256 threads
+ * tiling z; x is cut into chunks so that the grid is a whole number of waves
+ * of (SM count x resident CTAs). */
+static void launch_geometry(const void *kern, int nsm, int ncol4, int rows, int thr_override, int rpc_override,
+                            dim3 *grid, dim3 *block, int *rows_per_cta)
+{
+    int nthreads = ncol4 >= 256 ? 256 : ((ncol4 + 31) / 32) * 32;
+    if (thr_override > 0) nthreads = thr_override;
+    if (nthreads < 32) nthreads = 32;
+    int gx = (ncol4 + nthreads - 1) / nthreads;
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    long long cap = (long long)nsm * occ;
+    int rpc;
+    if (rpc_override > 0) {
+        rpc = rpc_override;
+    } else {
+        double waves = (double)gx * rows / ((double)cap * 96.0);
+        long long k = (long long)(waves + 0.5);
+        if (k < 1) k = 1;
+        long long gy = k * cap / gx;
+        if (gy < 1) gy = 1;
+        rpc = (int)((rows + gy - 1) / gy);
+        if (rpc < 8) rpc = 8;
+    }
+    int gy = (rows + rpc - 1) / rpc;
+    *grid = dim3(gx, gy < 1 ? 1 : gy, 1);
+    *block = dim3(nthreads, 1, 1);
+    *rows_per_cta = rpc;
+}
+
+static void base_args(const fdw_ctx *c, int pair, StepArgs *a)
+{
+    memset(a, 0, sizeof(*a));
+    const Field &n = c->f[c->newest[pair]], &o = c->f[c->older[pair]];
+    a->p = n.r0;
+    a->pp = o.r0;
+    a->vdt = c->vdt;
+    a->pitch = c->pitch;
+    a->ncol4 = c->ncol4;
+    a->grow0 = c->gx0;
+    a->lap_i0 = c->lap_i0; a->lap_i1 = c->lap_i1; a->lap_j0 = c->lap_j0; a->lap_j1 = c->lap_j1;
+    a->upd_j1 = c->upd_j1;
+    a->nze = c->nze;
+    memcpy(a->cz, c->cz, sizeof a->cz);
+    memcpy(a->cx, c->cx, sizeof a->cx);
+    a->dz2inv = c->dz2inv;
+    a->dx2inv = c->dx2inv;
+    a->taper_on = 0;
+    a->np = n.pend;
+    a->no = o.pend;
+    a->tz = c->tz;
+    a->tx = c->tx;
+    a->tx_jlim = c->tx_jlim; a->tz_ilim = c->tz_ilim;
+    a->tap_jlo = c->tap_jlo; a->tap_jhi = c->tap_jhi; a->tap_ilo = c->tap_ilo; a->tap_ihi = c->tap_ihi;
+    memcpy(a->src_w, c->src_w, sizeof a->src_w);
+    a->row0 = 0;
+    int hi = c->upd_i1 - c->gx0;
+    a->row1 = hi < c->nloc ? (hi < 0 ? 0 : hi) : c->nloc;
+}
+
+static int launch_step(fdw_ctx *c, StepArgs *a, int recipe, int epi)
+{
+    const void *k = step_kernel(c->prm.order, recipe, epi);
+    if (!k) {
+        fdw_set_error("no kernel for order %d recipe %d epilogue %d", c->prm.order, recipe, epi);
+        return FDW_ERR_UNSUPPORTED;
+    }
+    int rows = a->row1 - a->row0;
+    if (rows <= 0 || a->ncol4 <= 0) return FDW_OK;
+    dim3 grid, block;
+    launch_geometry(k, c->nsm, a->ncol4, rows, c->threads_override, c->rows_per_cta_override, &grid, &block,
+                    &a->rows_per_cta);
+    void *params[] = {a};
+    CU(cudaLaunchKernel(k, grid, block, params, 0, c->stream));
+    c->launches++;
+    return FDW_OK;
+}
+
+static void set_source_args(const fdw_ctx *c, StepArgs *a, int it)
+{
+    a->src_on = 1;
+    a->src_gi = c->sx;
+    a->src_j = c->sz;
+    a->src_rad = c->src_kind == FDW_SRC_GAUSS7 ? 3 : 0;
+    a->src_amp = (it >= 0 && it < (int)c->wavelet.size()) ? c->wavelet[it] : 0.0f;
+}
+
+/* one propagation step of `pair` with the context's sponge and step ordering.
+ * fill(a) lets the caller add epilogue arguments. */
+template <class Fill>
+static int step_pair(fdw_ctx *c, int pair, int recipe, int epi, bool sponge, bool source, int it, Fill fill)
+{
+    Field &n = c->f[c->newest[pair]], &o = c->f[c->older[pair]];
+    const bool tap = sponge && c->prm.taper != FDW_TAPER_NONE;
+    if (tap && c->prm.family == FDW_FAMILY_GPU) { /* sponge first: fd-code.cu:264 */
+        n.pend++;
+        o.pend++;
+    }
+    StepArgs a;
+    base_args(c, pair, &a);
+    a.taper_on = (n.pend || o.pend) ? 1 : 0;
+    if (source) set_source_args(c, &a, it);
+    fill(a);
+    CHECK(launch_step(c, &a, recipe, epi));
+    o.pend = 0; /* freshly written level */
+    if (tap && c->prm.family == FDW_FAMILY_CPU) { /* sponge last: mod_main.cpp:155-156 */
+        o.pend = 1;
+        n.pend++;
+    }
+    int t = c->newest[pair];
+    c->newest[pair] = c->older[pair];
+    c->older[pair] = t;
+    return FDW_OK;
+}
+
+static int materialize(fdw_ctx *c, Field &f)
+{
+    if (f.pend == 0) return FDW_OK;
+    int lo = -GUARD, hi = c->nloc + GUARD;
+    if (c->gx0 + lo < 0) lo = -c->gx0;
+    if (c->gx0 + hi > c->nxe) hi = c->nxe - c->gx0;
+    dim3 block(128), grid((c->nze + 127) / 128, hi - lo);
+    float *r0 = f.r0;
+    long long pitch = c->pitch;
+    const float *tz = c->tz, *tx = c->tx;
+    int cnt = f.pend;
+    void *params[] = {&r0, &pitch, &c->nze, &lo, &hi, &c->gx0, &tz, &tx, &c->tx_jlim, &c->tz_ilim, &cnt};
+    CU(cudaLaunchKernel(FDW_KPTR(k_materialize, thunk_materialize), grid, block, params, 0, c->stream));
+    c->launches++;
+    f.pend = 0;
+    return FDW_OK;
+}
+
+static int field_alloc(fdw_ctx *c, Field *f)
+{
+    CU(cudaMalloc(&f->base, c->field_elems * sizeof(float)));
+    CU(cudaMemsetAsync(f->base, 0, c->field_elems * sizeof(float), c->stream));
+    f->r0 = f->base + (size_t)(GUARD + 1) * c->pitch;
+    f->pend = 0;
+    return FDW_OK;
+}
+
+static int field_zero(fdw_ctx *c, Field *f)
+{
+    CU(cudaMemsetAsync(f->base, 0, c->field_elems * sizeof(float), c->stream));
+    f->pend = 0;
+    return FDW_OK;
+}
+
+/* host [nxe][nze] rows gx0.. -> device local rows (optionally with ghost rows) */
+static int field_h2d(fdw_ctx *c, float *r0, const float *host, int ghost)
+{
+    int lo = ghost ? -GUARD : 0, hi = c->nloc + (ghost ? GUARD : 0);
+    if (c->gx0 + lo < 0) lo = -c->gx0;
+    if (c->gx0 + hi > c->nxe) hi = c->nxe - c->gx0;
+    CU(cudaMemcpy2DAsync(r0 + (long long)lo * c->pitch, c->pitch * sizeof(float),
+                         host + (size_t)(c->gx0 + lo) * c->nze, (size_t)c->nze * sizeof(float),
+                         (size_t)c->nze * sizeof(float), hi - lo, cudaMemcpyHostToDevice, c->stream));
+    return FDW_OK;
+}
+
+static int field_d2h(fdw_ctx *c, const float *r0, float *host)
+{
+    CU(cudaMemcpy2DAsync(host + (size_t)c->gx0 * c->nze, (size_t)c->nze * sizeof(float), r0,
+                         c->pitch * sizeof(float), (size_t)c->nze * sizeof(float), c->nloc,
+                         cudaMemcpyDeviceToHost, c->stream));
+    return FDW_OK;
+}
+
+/* ------------------------------------------------------------------ create / destroy */
+extern "C" int fdw_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static void build_sponge_tables(fdw_ctx *c, std::vector<float> &tz, std::vector<float> &tx)
+{
+    const fdw_params &p = c->prm;
+    std::vector<float> tabx(p.nxb > 0 ? p.nxb : 1), tabz(p.nzb > 0 ? p.nzb : 1);
+    fdw_taper_table(p.nxb, p.fac, p.family, tabx.data());
+    fdw_taper_table(p.nzb, p.fac, p.family, tabz.data());
+    tz.assign((size_t)c->pitch + 8, 1.0f); /* index 4 + j */
+    tx.assign((size_t)c->nloc + 2 * GUARD, 1.0f); /* index GUARD + local row */
+    c->tx_jlim = INT_MAX; c->tz_ilim = INT_MAX;
+    c->tap_jlo = INT_MIN; c->tap_jhi = INT_MAX; c->tap_ilo = INT_MIN; c->tap_ihi = INT_MAX;
+    if (p.taper == FDW_TAPER_NONE) return;
+    int nzb_eff = p.nzb;
+    if (p.taper == FDW_TAPER_TOP && p.compat_extents) {
+        nzb_eff = (p.nzb / 8) * 8;            /* gridBorder_z, fd-code.cu:192-195 */
+        c->tz_ilim = (c->nxe / 8) * 8;        /* z factor only on launched rows */
+    }
+    for (int j = 0; j < nzb_eff; j++) tz[4 + j] = tabz[j];
+    if (p.taper == FDW_TAPER_FOUR)
+        for (int j = p.nz + p.nzb; j < c->nze; j++) tz[4 + j] = tabz[c->nze - 1 - j];
+    for (int lr = -GUARD; lr < c->nloc + GUARD; lr++) {
+        int gi = c->gx0 + lr;
+        if (gi < 0 || gi >= c->nxe) continue;
+        if (gi < p.nxb) tx[GUARD + lr] = tabx[gi];
+        else if (gi >= c->nxe - p.nxb) tx[GUARD + lr] = tabx[c->nxe - 1 - gi];
+    }
+    if (p.taper == FDW_TAPER_TOP) {
+        c->tx_jlim = nzb_eff; /* x factor only on the two top corners */
+        c->tap_jlo = nzb_eff;
+    } else {
+        c->tap_jlo = p.nzb; c->tap_jhi = p.nz + p.nzb;
+        c->tap_ilo = p.nxb; c->tap_ihi = p.nx + p.nxb;
+    }
+}
+
+extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
+{
+    if (!prm || !out) { fdw_set_error("fdw_create: null argument"); return FDW_ERR_ARG; }
+    *out = nullptr;
+    if (prm->nx < 1 || prm->nz < 1 || prm->nxb < 0 || prm->nzb < 0) {
+        fdw_set_error("fdw_create: bad grid %dx%d border %d,%d", prm->nx, prm->nz, prm->nxb, prm->nzb);
+        return FDW_ERR_ARG;
+    }
+    if (prm->order != 2 && prm->order != 4 && prm->order != 6 && prm->order != 8) {
+        fdw_set_error("fdw_create: order %d not supported on the device (2,4,6,8)", prm->order);
+        return FDW_ERR_UNSUPPORTED;
+    }
+    int ndev = fdw_device_count();
+    if (ndev < 1 || prm->device < 0 || prm->device >= ndev) {
+        fdw_set_error("fdw_create: CUDA device %d not available (%d visible); libfdwave has no CPU path",
+                      prm->device, ndev);
+        return FDW_ERR_CUDA;
+    }
+    fdw_ctx *c = new fdw_ctx();
+    c->prm = *prm;
+    c->nxe = prm->nx + 2 * prm->nxb;
+    c->nze = prm->nz + 2 * prm->nzb;
+    c->H = prm->order / 2;
+    c->gx0 = 0;
+    c->nloc = c->nxe;
+    if (prm->slab_x1 > prm->slab_x0) {
+        if (prm->slab_x0 < 0 || prm->slab_x1 > c->nxe) {
+            delete c;
+            fdw_set_error("fdw_create: slab [%d,%d) outside [0,%d)", prm->slab_x0, prm->slab_x1, c->nxe);
+            return FDW_ERR_ARG;
+        }
+        c->gx0 = prm->slab_x0;
+        c->nloc = prm->slab_x1 - prm->slab_x0;
+    }
+    c->pitch = pitch_for(c->nze);
+    c->rows_alloc = (size_t)c->nloc + 2 * GUARD + 2;
+    c->field_elems = c->rows_alloc * (size_t)c->pitch;
+    int rc = bind(c);
+    if (rc != FDW_OK) { delete c; return rc; }
+    cudaDeviceProp dp;
+    if (cudaGetDeviceProperties(&dp, prm->device) != cudaSuccess) { delete c; fdw_set_error("cudaGetDeviceProperties failed"); return FDW_ERR_CUDA; }
+    c->nsm = dp.multiProcessorCount;
+    if (const char *e = getenv("FDW_ROWS_PER_CTA")) c->rows_per_cta_override = atoi(e);
+    if (const char *e = getenv("FDW_THREADS")) c->threads_override = atoi(e);
+
+    /* coefficients and scalars: fd-code.cu:203-217 / fd.c:12-16 */
+    float coefs[9];
+    fdw_calc_coefs(prm->order, prm->family, coefs);
+    c->dx2inv = (1. / prm->dx) * (1. / prm->dx);
+    c->dz2inv = (1. / prm->dz) * (1. / prm->dz);
+    c->dt2 = prm->dt * prm->dt;
+    memset(c->cz, 0, sizeof c->cz);
+    memset(c->cx, 0, sizeof c->cx);
+    for (int k = 0; k <= prm->order; k++) {
+        if (prm->recipe == FDW_RECIPE_C) {
+            c->cz[k] = c->cx[k] = coefs[k];
+        } else {
+            c->cz[k] = c->dz2inv * coefs[k];
+            c->cx[k] = c->dx2inv * coefs[k];
+        }
+    }
+    fdw_ptsrc_weights(c->src_w);
+
+    /* extents (quirk Q1 when asked for) */
+    const int h = c->H;
+    if (prm->compat_extents) {
+        const int ux = (c->nxe / 8) * 8, uz = (c->nze / 8) * 8;
+        c->upd_i1 = ux; c->upd_j1 = uz;
+        c->lap_i1 = h + ux < c->nxe - h ? h + ux : c->nxe - h;
+        c->lap_j1 = h + uz < c->nze - h ? h + uz : c->nze - h;
+    } else {
+        c->upd_i1 = c->nxe; c->upd_j1 = c->nze;
+        c->lap_i1 = c->nxe - h; c->lap_j1 = c->nze - h;
+    }
+    c->lap_i0 = c->lap_j0 = h;
+    c->ncol4 = (c->upd_j1 + 3) / 4;
+
+#define TRY(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            fdw_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+            fdw_destroy(c);                                                                    \
+            return e_ == cudaErrorMemoryAllocation ? FDW_ERR_NOMEM : FDW_ERR_CUDA;             \
+        }                                                                                      \
+    } while (0)
+    TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    TRY(cudaEventCreate(&c->ev0));
+    TRY(cudaEventCreate(&c->ev1));
+    for (int k = 0; k < 4; k++) {
+        rc = field_alloc(c, &c->f[k]);
+        if (rc != FDW_OK) { fdw_destroy(c); return rc; }
+    }
+    c->newest[0] = 0; c->older[0] = 1; c->newest[1] = 2; c->older[1] = 3;
+    TRY(cudaMalloc(&c->vdt_base, c->field_elems * sizeof(float)));
+    TRY(cudaMemsetAsync(c->vdt_base, 0, c->field_elems * sizeof(float), c->stream));
+    c->vdt = c->vdt_base + (size_t)(GUARD + 1) * c->pitch;
+    std::vector<float> tz, tx;
+    build_sponge_tables(c, tz, tx);
+    TRY(cudaMalloc(&c->tz_base, tz.size() * sizeof(float)));
+    TRY(cudaMalloc(&c->tx_base, tx.size() * sizeof(float)));
+    TRY(cudaMemcpyAsync(c->tz_base, tz.data(), tz.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    TRY(cudaMemcpyAsync(c->tx_base, tx.data(), tx.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->tz = c->tz_base + 4;
+    c->tx = c->tx_base + GUARD;
+    const size_t img_elems = (size_t)prm->nx * c->pitch;
+    TRY(cudaMalloc(&c->img, img_elems * sizeof(float)));
+    TRY(cudaMemsetAsync(c->img, 0, img_elems * sizeof(float), c->stream));
+    if (prm->history) {
+        if (prm->nt < 1) { fdw_destroy(c); fdw_set_error("fdw_create: history needs nt"); return FDW_ERR_ARG; }
+        TRY(cudaMalloc(&c->hist, (size_t)prm->nt * img_elems * sizeof(float)));
+    }
+    TRY(cudaStreamSynchronize(c->stream)); /* the staging vectors go out of scope */
+#undef TRY
+    *out = c;
+    return FDW_OK;
+}
+
+extern "C" void fdw_destroy(fdw_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 4; k++) cudaFree(c->f[k].base);
+    cudaFree(c->vdt_base); cudaFree(c->tz_base); cudaFree(c->tx_base);
+    cudaFree(c->hist); cudaFree(c->img); cudaFree(c->dobs_d); cudaFree(c->rec_d);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int fdw_set_stream(fdw_ctx *c, void *s)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    if (s) {
+        c->stream = (cudaStream_t)s;
+    } else {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return FDW_OK;
+}
+
+extern "C" int fdw_sync(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_set_v2(fdw_ctx *c, const float *v2)
+{
+    if (!c || !v2) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CHECK(field_h2d(c, c->vdt, v2, 1));
+    /* fl32(v2*dt2): the first of the two float multiplies of v2*dt2*lap (fd-code.cu:89) */
+    long long n = (long long)c->field_elems;
+    void *params[] = {&c->vdt_base, &n, &c->dt2};
+    CU(cudaLaunchKernel(FDW_KPTR(k_scale_rows, thunk_scale_rows), dim3((unsigned)((n + 255) / 256)), dim3(256), params,
+                        0, c->stream));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_set_wavelet(fdw_ctx *c, const float *s, int nt)
+{
+    if (!c || !s || nt < 0) return FDW_ERR_ARG;
+    c->wavelet.assign(s, s + nt);
+    return FDW_OK;
+}
+
+extern "C" int fdw_set_source(fdw_ctx *c, int sx, int sz, int kind)
+{
+    if (!c || (kind != FDW_SRC_POINT && kind != FDW_SRC_GAUSS7)) return FDW_ERR_ARG;
+    c->sx = sx; c->sz = sz; c->src_kind = kind;
+    return FDW_OK;
+}
+
+extern "C" int fdw_fields_zero(fdw_ctx *c, int pair)
+{
+    if (!c || pair < 0 || pair > 1) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CHECK(field_zero(c, &c->f[c->newest[pair]]));
+    CHECK(field_zero(c, &c->f[c->older[pair]]));
+    if (pair == 0) c->saved_valid = false;
+    return FDW_OK;
+}
+
+extern "C" int fdw_fields_upload(fdw_ctx *c, int pair, const float *newest, const float *older)
+{
+    if (!c || pair < 0 || pair > 1 || !newest || !older) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    Field &n = c->f[c->newest[pair]], &o = c->f[c->older[pair]];
+    CHECK(field_h2d(c, n.r0, newest, 1));
+    CHECK(field_h2d(c, o.r0, older, 1));
+    n.pend = o.pend = 0;
+    return FDW_OK;
+}
+
+extern "C" int fdw_fields_download(fdw_ctx *c, int pair, float *newest, float *older)
+{
+    if (!c || pair < 0 || pair > 1) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    Field &n = c->f[c->newest[pair]], &o = c->f[c->older[pair]];
+    if (newest) { CHECK(materialize(c, n)); CHECK(field_d2h(c, n.r0, newest)); }
+    if (older) { CHECK(materialize(c, o)); CHECK(field_d2h(c, o.r0, older)); }
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_advance(fdw_ctx *c, int it0, int nsteps)
+{
+    if (!c || nsteps < 0) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    for (int it = it0; it < it0 + nsteps; it++)
+        CHECK(step_pair(c, 0, c->prm.recipe, 0, true, !c->wavelet.empty(), it, [](StepArgs &) {}));
+    return FDW_OK;
+}
+
+extern "C" int fdw_propagate(fdw_ctx *c, float *newest, float *older, int it0, int nsteps)
+{
+    if (!c || !newest || !older) return FDW_ERR_ARG;
+    CHECK(fdw_fields_upload(c, 0, newest, older));
+    CHECK(fdw_advance(c, it0, nsteps));
+    return fdw_fields_download(c, 0, newest, older);
+}
+
+/* ------------------------------------------------------------------ pipelines */
+extern "C" int fdw_forward(fdw_ctx *c, int sx, int sz, float *P, float *PP)
+{
+    if (!c) return FDW_ERR_ARG;
+    if (c->wavelet.size() < (size_t)c->prm.nt || c->prm.nt < 1) {
+        fdw_set_error("fdw_forward: set params.nt and a wavelet of nt samples first");
+        return FDW_ERR_STATE;
+    }
+    CHECK(fdw_fields_zero(c, 0));
+    CHECK(fdw_set_source(c, sx, sz, FDW_SRC_POINT));
+    CHECK(fdw_advance(c, 0, c->prm.nt));
+    /* d_p (older, sponged once in the last iteration) and d_pp (newest), fd-code.cu:285-286 */
+    CHECK(materialize(c, c->f[c->newest[0]]));
+    CHECK(materialize(c, c->f[c->older[0]]));
+    c->saved_valid = true;
+    if (P || PP) CHECK(fdw_fields_download(c, 0, PP, P));
+    return FDW_OK;
+}
+
+static int ensure_buffer(float **buf, size_t *cap, size_t need)
+{
+    if (*cap >= need) return FDW_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(buf, need * sizeof(float)));
+    *cap = need;
+    return FDW_OK;
+}
+
+static int image_download(fdw_ctx *c, float *imloc)
+{
+    const fdw_params &p = c->prm;
+    CU(cudaMemcpy2DAsync(imloc, (size_t)p.nz * sizeof(float), c->img + p.nzb, c->pitch * sizeof(float),
+                         (size_t)p.nz * sizeof(float), p.nx, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_backward(fdw_ctx *c, const float *P, const float *PP, const float *dobs, int gz, float *imloc)
+{
+    if (!c || !dobs || !imloc || ((P == nullptr) != (PP == nullptr))) return FDW_ERR_ARG;
+    const fdw_params &p = c->prm;
+    const int nt = p.nt;
+    if (nt < 1) { fdw_set_error("fdw_backward: params.nt not set"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    if (P) {
+        CHECK(fdw_fields_upload(c, 0, PP, P)); /* newest = PP = u(T), older = P = u(T-1) */
+    } else if (!c->saved_valid) {
+        fdw_set_error("fdw_backward: no saved levels on the device (run fdw_forward first)");
+        return FDW_ERR_STATE;
+    }
+    /* time-reversed roles: S_0 = PP, S_1 = P (fd-code.cu:304-314) */
+    int s_pp = c->newest[0], s_p = c->older[0];
+    CHECK(fdw_fields_zero(c, 1));
+    CU(cudaMemsetAsync(c->img, 0, (size_t)p.nx * c->pitch * sizeof(float), c->stream));
+    const size_t ntr = (size_t)p.nx * nt;
+    CHECK(ensure_buffer(&c->dobs_d, &c->dobs_cap, ntr));
+    CU(cudaMemcpyAsync(c->dobs_d, dobs, ntr * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const int nrec = p.compat_extents ? (p.nx < c->upd_i1 ? p.nx : c->upd_i1) : p.nx;
+    int cur = s_pp, prev1 = -1, prev2 = -1;
+    for (int it = 0; it < nt; it++) {
+        if (it == 0) {
+            cur = s_pp;
+        } else if (it == 1) {
+            prev1 = s_pp;
+            cur = s_p;
+        } else {
+            /* same update run backwards in time: no sponge, no source (fd-code.cu:317-318) */
+            prev2 = prev1;
+            prev1 = cur;
+            c->newest[0] = prev1;
+            c->older[0] = prev2;
+            CHECK(step_pair(c, 0, p.recipe, 0, false, false, it, [](StepArgs &) {}));
+            cur = prev2;
+        }
+        const float *srcfield = c->f[cur].r0;
+        CHECK(step_pair(c, 1, p.recipe, fdw::EPI_INJECT | fdw::EPI_IMG_FIELD, true, false, it, [&](StepArgs &a) {
+            a.dobs = c->dobs_d; a.dobs_base = 0; a.dobs_len = (long long)ntr;
+            a.inj_gi0 = p.nxb; a.inj_n = nrec; a.inj_j = gz; a.inj_nt = nt; a.inj_tidx = nt - 1 - it;
+            a.img = c->img; a.img_gi0 = p.nxb; a.img_n = nrec; a.img_field = srcfield;
+        }));
+    }
+    c->saved_valid = false;
+    return image_download(c, imloc);
+}
+
+extern "C" int fdw_model_shot(fdw_ctx *c, int sx, int sz, int gz, float *data)
+{
+    if (!c || !data) return FDW_ERR_ARG;
+    const fdw_params &p = c->prm;
+    const int nt = p.nt;
+    if (nt < 1 || c->wavelet.size() < (size_t)nt) { fdw_set_error("fdw_model_shot: nt / wavelet not set"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    CHECK(fdw_fields_zero(c, 0));
+    CHECK(fdw_set_source(c, sx, sz, FDW_SRC_GAUSS7));
+    const size_t ntr = (size_t)p.nx * nt;
+    CHECK(ensure_buffer(&c->rec_d, &c->rec_cap, ntr));
+    CU(cudaMemsetAsync(c->rec_d, 0, ntr * sizeof(float), c->stream));
+    for (int it = 0; it < nt; it++)
+        CHECK(step_pair(c, 0, p.recipe, fdw::EPI_RECORD, true, true, it, [&](StepArgs &a) {
+            a.rec = c->rec_d; a.rec_gi0 = p.nxb; a.rec_n = p.nx; a.rec_j = gz; a.rec_nt = nt; a.rec_it = it;
+        }));
+    CU(cudaMemcpyAsync(data, c->rec_d, ntr * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_rtm_shot_cpu(fdw_ctx *c, int sx, int sz, int gz, const float *dobs_all, int ns, int is,
+                                float *imloc)
+{
+    if (!c || !dobs_all || !imloc || ns < 1 || is < 0 || is >= ns) return FDW_ERR_ARG;
+    const fdw_params &p = c->prm;
+    const int nt = p.nt;
+    if (!c->hist) { fdw_set_error("fdw_rtm_shot_cpu: context created without params.history"); return FDW_ERR_STATE; }
+    if (nt < 1 || c->wavelet.size() < (size_t)nt) { fdw_set_error("fdw_rtm_shot_cpu: nt / wavelet not set"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    const size_t slice = (size_t)p.nx * c->pitch;
+    /* forward with history (rtm_main.cpp:166-188) */
+    CHECK(fdw_fields_zero(c, 0));
+    CHECK(fdw_set_source(c, sx, sz, FDW_SRC_POINT));
+    for (int it = 0; it < nt; it++)
+        CHECK(step_pair(c, 0, p.recipe, fdw::EPI_HSTORE, true, true, it, [&](StepArgs &a) {
+            a.hist_w = c->hist + (size_t)it * slice; a.hist_gi0 = p.nxb; a.hist_n = p.nx;
+        }));
+    /* backward + imaging on the fly (rtm_main.cpp:196-229): imloc += swf[nt-1-it]*rwf[it],
+     * it ascending -- the same float summation order as the reference's third loop */
+    CHECK(fdw_fields_zero(c, 0));
+    CU(cudaMemsetAsync(c->img, 0, slice * sizeof(float), c->stream));
+    const size_t ntot = (size_t)ns * p.nx * nt;
+    CHECK(ensure_buffer(&c->dobs_d, &c->dobs_cap, ntot));
+    CU(cudaMemcpyAsync(c->dobs_d, dobs_all, ntot * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    for (int it = 0; it < nt; it++)
+        CHECK(step_pair(c, 0, p.recipe, fdw::EPI_INJECT | fdw::EPI_IMG_HIST, true, false, it, [&](StepArgs &a) {
+            a.dobs = c->dobs_d; a.dobs_base = (long long)is * p.nx * nt; a.dobs_len = (long long)ntot;
+            a.inj_gi0 = p.nzb; /* quirk Q5: rtm_main.cpp:202 offsets x by nzb */
+            a.inj_n = p.nx; a.inj_j = gz; a.inj_nt = nt; a.inj_tidx = nt - it; /* Q5: nt-it */
+            a.hist_r = c->hist + (size_t)(nt - 1 - it) * slice; a.hist_gi0 = p.nxb; a.hist_n = p.nx;
+            a.img = c->img; a.img_gi0 = p.nxb; a.img_n = p.nx;
+        }));
+    return image_download(c, imloc);
+}
+
+/* ------------------------------------------------------------------ stencil program */
+static int launch_lap(fdw_ctx *c, const float *src, float *dst)
+{
+    const void *k = lap_kernel(c->prm.order);
+    StepArgs a;
+    base_args(c, 0, &a);
+    a.p = src;
+    a.ncol4 = (c->nze + 3) / 4;
+    a.row0 = 0;
+    a.row1 = c->nloc;
+    a.lap_i1 = c->nxe - c->H; a.lap_j1 = c->nze - c->H; /* the stencil program rounds its grid up */
+    dim3 grid, block;
+    launch_geometry(k, c->nsm, a.ncol4, a.row1, c->threads_override, c->rows_per_cta_override, &grid, &block,
+                    &a.rows_per_cta);
+    void *params[] = {&a, &dst};
+    CU(cudaLaunchKernel(k, grid, block, params, 0, c->stream));
+    c->launches++;
+    return FDW_OK;
+}
+
+extern "C" int fdw_laplacian_device(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    return launch_lap(c, c->f[c->newest[0]].r0, c->f[c->older[0]].r0);
+}
+
+extern "C" int fdw_stencil(int order, int nxe, int nze, float dx, float dz, const float *in, float *out, int device)
+{
+    if (!in || !out || nxe < 1 || nze < 1) return FDW_ERR_ARG;
+    fdw_params p;
+    memset(&p, 0, sizeof p);
+    p.nx = nxe; p.nz = nze; p.order = order; p.dx = dx; p.dz = dz; p.dt = 1.0f; p.fac = 0.5f;
+    p.family = FDW_FAMILY_GPU; p.recipe = FDW_RECIPE_G; p.taper = FDW_TAPER_NONE; p.device = device;
+    fdw_ctx *c = nullptr;
+    CHECK(fdw_create(&p, &c));
+    int rc = field_h2d(c, c->f[0].r0, in, 0);
+    if (rc == FDW_OK) rc = launch_lap(c, c->f[0].r0, c->f[1].r0);
+    if (rc == FDW_OK) rc = field_d2h(c, c->f[1].r0, out);
+    if (rc == FDW_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        fdw_set_error("fdw_stencil: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = FDW_ERR_CUDA;
+    }
+    fdw_destroy(c);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ device-resident access */
+extern "C" int fdw_devinfo_get(fdw_ctx *c, fdw_devinfo *o)
+{
+    if (!c || !o) return FDW_ERR_ARG;
+    o->newest = c->f[c->newest[0]].r0;
+    o->older = c->f[c->older[0]].r0;
+    o->vdt = c->vdt;
+    o->pitch = c->pitch;
+    o->nloc = c->nloc; o->gx0 = c->gx0; o->nxe = c->nxe; o->nze = c->nze; o->guard = GUARD;
+    return FDW_OK;
+}
+
+extern "C" int fdw_mark_begin(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_mark_end(fdw_ctx *c, float *ms)
+{
+    if (!c || !ms) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return FDW_OK;
+}
+
+extern "C" long long fdw_launch_count(fdw_ctx *c) { return c ? c->launches : 0; }

@@ -1,0 +1,391 @@
+/*
+ * fdw_step_core.h -- per-thread body of the fused propagation kernel.
+ *
+ * One thread owns 4 consecutive z samples (one float4 column) and streams
+ * along x (the slow axis) holding the (order+1)-row x window of the newer
+ * time level in registers.  The z neighbours come from the two adjacent
+ * aligned float4 of the centre row (L1 hits: the neighbouring threads
+ * streamed them order/2 rows earlier).  Threads never exchange data and the
+ * older level is read and overwritten by its owning thread only, so the
+ * kernel is race-free without shared memory or barriers.
+ *
+ * What is fused (reference file:line):
+ *   Laplacian      kernel_lap   cuda_reference_RTM/src/fd-code.cu:53-78
+ *                  fd_step      dpct_gpu_rtm_domain_division/src/timestep/fd.c:28-37
+ *   leapfrog       kernel_time  fd-code.cu:80-92, fd.c:39-43
+ *   sponge         kernel_tapper fd-code.cu:94-117, taper_apply/2 taper.c:47-84
+ *                  (applied ON LOAD to raw stored levels: position-only
+ *                  factors, same sequence of float multiplies)
+ *   source         kernel_src fd-code.cu:119-122, ptsrc ptsrc.c:12-58
+ *   record         mod_main.cpp:159-161
+ *   back-injection kernel_sism fd-code.cu:124-131, rtm_main.cpp:201-203
+ *   imaging        kernel_img fd-code.cu:133-144, rtm_main.cpp:223-229
+ *   history        rtm_main.cpp:177-181 (store), :223-229 (read)
+ *
+ * The header compiles for the device (nvcc) and, for the CPU-only unit tests
+ * of the index/sponge/epilogue logic, for the host (tests/emu/).  The host
+ * build is test infrastructure; the product only ever runs the device build.
+ */
+#ifndef FDW_STEP_CORE_H
+#define FDW_STEP_CORE_H
+
+#ifdef __CUDACC__
+#define FDW_HD __host__ __device__ __forceinline__
+#define FDW_UNROLL _Pragma("unroll")
+#else
+#include <math.h>
+#define FDW_HD static inline
+#define FDW_UNROLL
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
+#endif
+
+namespace fdw {
+
+enum { RECIPE_G = 0, RECIPE_C = 1, RECIPE_FAST = 2 };
+enum { EPI_RECORD = 1, EPI_INJECT = 2, EPI_HSTORE = 4, EPI_IMG_HIST = 8, EPI_IMG_FIELD = 16 };
+enum { GUARD = 4 }; /* guard/ghost rows above and below every slab; >= order/2 */
+
+struct StepArgs {
+    const float *p;  /* newer level, local row 0 / column 0; stencil input, never written */
+    float *pp;       /* older level in, next level out (in place, own column only) */
+    const float *vdt; /* fl32(v2*dt2), same layout */
+    long long pitch; /* floats per row, multiple of 32, >= nze+4 */
+    int ncol4;       /* float4 columns that are updated */
+    int row0, row1;  /* local rows [row0,row1) handled by this launch */
+    int rows_per_cta;
+    int grow0;       /* global x index of local row 0 */
+    int lap_i0, lap_i1, lap_j0, lap_j1; /* Laplacian is non-zero only inside (global) */
+    int upd_j1;      /* columns j < upd_j1 are updated (row extent is clamped by the host) */
+    int nze;         /* valid columns per row */
+    float cz[9], cx[9]; /* G/FAST: premultiplied weights; C: both hold the raw weights */
+    float dz2inv, dx2inv;
+    /* sponge */
+    int taper_on;
+    int np, no;       /* multiplications pending on the newer / older level (0..2) */
+    const float *tz;  /* z factor per column, 4 valid entries before [0] and up to pitch+4 */
+    const float *tx;  /* x factor per local row, valid on [-GUARD, nloc+GUARD) */
+    int tx_jlim;      /* x factor applies to columns j < tx_jlim */
+    int tz_ilim;      /* z factor applies to global rows < tz_ilim */
+    int tap_jlo, tap_jhi; /* some factor != 1 only if j < tap_jlo or j >= tap_jhi ... */
+    int tap_ilo, tap_ihi; /* ... or global row < tap_ilo or >= tap_ihi */
+    /* source */
+    int src_on, src_gi, src_j, src_rad;
+    float src_amp;
+    float src_w[49];
+    /* receiver recording: rec[(gi-rec_gi0)*rec_nt + rec_it] = sample at column rec_j */
+    float *rec;
+    int rec_gi0, rec_n, rec_j, rec_nt, rec_it;
+    /* back-injection: pp_new[gi][inj_j] += dobs[dobs_base + (gi-inj_gi0)*inj_nt + inj_tidx] */
+    const float *dobs;
+    long long dobs_base, dobs_len;
+    int inj_gi0, inj_n, inj_j, inj_nt, inj_tidx;
+    /* forward history (rows rec. as full pitched rows of the interior x range) */
+    float *hist_w;
+    const float *hist_r;
+    int hist_gi0, hist_n;
+    /* image, pitched like the field, row 0 = global row img_gi0 */
+    float *img;
+    int img_gi0, img_n;
+    const float *img_field; /* EPI_IMG_FIELD: reconstructed source level, field layout */
+};
+
+FDW_HD float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+FDW_HD void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+#ifdef __CUDA_ARCH__
+FDW_HD float4 ld4_stream(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+FDW_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+FDW_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+FDW_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+/* fl32( fl64( 2.*p - pp ) + t ): 2.*p is exact, so the DFMA rounds once exactly
+ * like the reference's separate DMUL/DADD pair (fd-code.cu:89, fd.c:41). */
+FDW_HD float leap(float p, float pp, float t)
+{
+    double d = __fma_rn(2.0, (double)p, -(double)pp);
+    return __double2float_rn(__dadd_rn(d, (double)t));
+}
+#else
+FDW_HD float4 ld4_stream(const float *p) { return ld4(p); }
+FDW_HD float fmul(float a, float b) { return a * b; }
+FDW_HD float fadd(float a, float b) { return a + b; }
+FDW_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+FDW_HD float leap(float p, float pp, float t)
+{
+    double d = 2.0 * (double)p - (double)pp;
+    return (float)(d + (double)t);
+}
+#endif
+
+template <int K> FDW_HD float get(const float4 &v) { return K == 0 ? v.x : K == 1 ? v.y : K == 2 ? v.z : v.w; }
+FDW_HD float getk(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+/* sponge applied cnt times to one float4 whose 4 columns have z factors zf[0..3];
+ * the x factor xf applies to the columns flagged in xon (bit k).  Each
+ * application is (v*Z)*X, the order of kernel_tapper / taper_apply. */
+FDW_HD float4 tap4(float4 v, const float *zf, unsigned xon, float xf, bool zon, int cnt)
+{
+    float e[4] = {v.x, v.y, v.z, v.w};
+    for (int c = 0; c < cnt; c++) {
+        FDW_UNROLL
+        for (int k = 0; k < 4; k++) {
+            e[k] = fmul(e[k], zon ? zf[k] : 1.0f);
+            e[k] = fmul(e[k], ((xon >> k) & 1u) ? xf : 1.0f);
+        }
+    }
+    return make_float4(e[0], e[1], e[2], e[3]);
+}
+
+/* does this CTA touch a point whose sponge factor differs from 1 ? */
+FDW_HD bool block_needs_taper(const StepArgs &a, int bx, int by, int bdim, int half)
+{
+    if (!a.taper_on) return false;
+    int jlo = bx * bdim * 4 - 4, jhi = (bx + 1) * bdim * 4 + 4;
+    if (jlo < a.tap_jlo || jhi > a.tap_jhi) return true;
+    int rb = a.row0 + by * a.rows_per_cta;
+    int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
+    int glo = a.grow0 + rb - half, ghi = a.grow0 + re + half;
+    return glo < a.tap_ilo || ghi > a.tap_ihi;
+}
+
+template <int ORDER, int RECIPE, bool TAPER, int EPI>
+FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
+{
+    constexpr int H = ORDER / 2, W = ORDER + 1;
+    const int q = bx * bdim + tid;
+    if (q >= a.ncol4) return;
+    const int j0 = q * 4;
+    const int rb = a.row0 + by * a.rows_per_cta;
+    const int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
+    if (rb >= re) return;
+    const long long pitch = a.pitch;
+
+    /* per-thread column predicates */
+    unsigned mlap = 0, mupd = 0;
+    FDW_UNROLL
+    for (int k = 0; k < 4; k++) {
+        if (j0 + k >= a.lap_j0 && j0 + k < a.lap_j1) mlap |= 1u << k;
+        if (j0 + k < a.upd_j1) mupd |= 1u << k;
+    }
+
+    /* sponge factors of the 12 columns j0-4 .. j0+7 */
+    float zf[12];
+    unsigned xon = 0;
+    if (TAPER) {
+        FDW_UNROLL
+        for (int m = 0; m < 12; m++) {
+            zf[m] = a.tz[j0 - 4 + m];
+            if (j0 - 4 + m < a.tx_jlim) xon |= 1u << m;
+        }
+    }
+
+    const float *pc = a.p + j0 + (long long)(rb - H) * pitch; /* row being streamed in */
+    float *ppc = a.pp + j0 + (long long)rb * pitch;
+    const float *vc = a.vdt + j0 + (long long)rb * pitch;
+
+    float4 w[W];
+    FDW_UNROLL
+    for (int s = 0; s < 2 * H; s++) {
+        w[s] = ld4(pc);
+        if (TAPER) {
+            int lr = rb - H + s;
+            w[s] = tap4(w[s], zf + 4, xon >> 4, a.tx[lr], a.grow0 + lr < a.tz_ilim, a.np);
+        }
+        pc += pitch;
+    }
+
+    for (int r = rb; r < re; r += W) {
+        FDW_UNROLL
+        for (int u = 0; u < W; u++) {
+            const int lr = r + u; /* local row being updated */
+            if (lr < re) {
+                const int gi = a.grow0 + lr;
+                float4 wn = ld4(pc); /* row lr+H */
+                const float *ctr = pc - (long long)H * pitch;
+                float4 l4 = ld4(ctr - 4), r4 = ld4(ctr + 4);
+                float4 o4 = ld4(ppc);
+                float4 v4 = ld4_stream(vc);
+                if (TAPER) {
+                    const float xf = a.tx[lr];
+                    const bool zon = gi < a.tz_ilim;
+                    wn = tap4(wn, zf + 4, xon >> 4, a.tx[lr + H], gi + H < a.tz_ilim, a.np);
+                    l4 = tap4(l4, zf, xon, xf, zon, a.np);
+                    r4 = tap4(r4, zf + 8, xon >> 8, xf, zon, a.np);
+                    o4 = tap4(o4, zf + 4, xon >> 4, xf, zon, a.no);
+                }
+                w[(u + 2 * H) % W] = wn;
+                const float4 c4 = w[(u + H) % W];
+                const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float oo[4] = {o4.x, o4.y, o4.z, o4.w};
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+                const unsigned ml = (gi >= a.lap_i0 && gi < a.lap_i1) ? mlap : 0u;
+                float res[4];
+                FDW_UNROLL
+                for (int k = 0; k < 4; k++) {
+                    float lap;
+                    if (RECIPE == RECIPE_G) {
+                        /* two accumulators, ascending io, summed last (fd-code.cu:66-72).
+                         * The reference's "0 +" first add is dropped: it can only change
+                         * the sign of an all-zero sum, which provably never reaches pp. */
+                        float az = fmul(za[4 + k - H], a.cz[0]);
+                        float ax = fmul(getk(w[(u + 0) % W], k), a.cx[0]);
+                        FDW_UNROLL
+                        for (int io = 1; io <= ORDER; io++) {
+                            az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
+                            ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
+                        }
+                        lap = fadd(az, ax);
+                    } else if (RECIPE == RECIPE_C) {
+                        /* one accumulator, z tap then x tap, (p*c)*d2inv (fd.c:30-33) */
+                        float acm = fmul(fmul(za[4 + k - H], a.cz[0]), a.dz2inv);
+                        acm = fadd(acm, fmul(fmul(getk(w[(u + 0) % W], k), a.cx[0]), a.dx2inv));
+                        FDW_UNROLL
+                        for (int io = 1; io <= ORDER; io++) {
+                            acm = fadd(acm, fmul(fmul(za[4 + k - H + io], a.cz[io]), a.dz2inv));
+                            acm = fadd(acm, fmul(fmul(getk(w[(u + io) % W], k), a.cx[io]), a.dx2inv));
+                        }
+                        lap = acm;
+                    } else {
+                        /* FAST: symmetric pairs + FMA; tolerance-checked, not bit-checked */
+                        float s = fmul(cc[k], a.cz[H] + a.cx[H]);
+                        FDW_UNROLL
+                        for (int d = 1; d <= H; d++) {
+                            s = ffma(a.cz[H + d], za[4 + k - d] + za[4 + k + d], s);
+                            s = ffma(a.cx[H + d], getk(w[(u + H - d) % W], k) + getk(w[(u + H + d) % W], k), s);
+                        }
+                        lap = s;
+                    }
+                    if (!((ml >> k) & 1u)) lap = 0.0f;
+                    if (RECIPE == RECIPE_FAST)
+                        res[k] = ffma(vv[k], lap, 2.0f * cc[k] - oo[k]);
+                    else
+                        res[k] = leap(cc[k], oo[k], fmul(vv[k], lap));
+                }
+
+                /* ---- source (after the update, before the sponge: both families) */
+                if (a.src_on && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad &&
+                    j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad) {
+                    FDW_UNROLL
+                    for (int k = 0; k < 4; k++) {
+                        int dj = j0 + k - a.src_j, di = gi - a.src_gi;
+                        if (dj >= -a.src_rad && dj <= a.src_rad && j0 + k < a.nze) {
+                            float amp = a.src_rad ? fmul(a.src_amp, a.src_w[(di + 3) * 7 + (dj + 3)]) : a.src_amp;
+                            res[k] = fadd(res[k], amp);
+                        }
+                    }
+                }
+                /* ---- receiver back-injection */
+                if ((EPI & EPI_INJECT) && gi >= a.inj_gi0 && gi < a.inj_gi0 + a.inj_n && a.inj_j >= j0 &&
+                    a.inj_j < j0 + 4) {
+                    long long idx = a.dobs_base + (long long)(gi - a.inj_gi0) * a.inj_nt + a.inj_tidx;
+                    float s = (idx >= 0 && idx < a.dobs_len) ? a.dobs[idx] : 0.0f;
+                    FDW_UNROLL
+                    for (int k = 0; k < 4; k++)
+                        if (j0 + k == a.inj_j) res[k] = fadd(res[k], s);
+                }
+                /* ---- columns outside the reference's truncated launch extent keep their value */
+                if (mupd != 0xFu) {
+                    const float4 raw = ld4(ppc);
+                    FDW_UNROLL
+                    for (int k = 0; k < 4; k++)
+                        if (!((mupd >> k) & 1u)) res[k] = getk(raw, k);
+                }
+                st4(ppc, make_float4(res[0], res[1], res[2], res[3]));
+
+                /* ---- seismogram sample: the newer level after one more sponge pass */
+                if ((EPI & EPI_RECORD) && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n && a.rec_j >= j0 &&
+                    a.rec_j < j0 + 4) {
+                    float4 s4 = c4;
+                    if (TAPER) s4 = tap4(s4, zf + 4, xon >> 4, a.tx[lr], gi < a.tz_ilim, 1);
+                    a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + a.rec_it] = getk(s4, a.rec_j - j0);
+                }
+                /* ---- forward history: interior rows of the newer level (sponge factor there is 1) */
+                if ((EPI & EPI_HSTORE) && gi >= a.hist_gi0 && gi < a.hist_gi0 + a.hist_n)
+                    st4(a.hist_w + (long long)(gi - a.hist_gi0) * pitch + j0, c4);
+                /* ---- imaging condition */
+                if ((EPI & EPI_IMG_HIST) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
+                    float *ip = a.img + (long long)(gi - a.img_gi0) * pitch + j0;
+                    const float4 s4 = ld4_stream(a.hist_r + (long long)(gi - a.hist_gi0) * pitch + j0);
+                    float4 im = ld4(ip);
+                    im.x = fadd(im.x, fmul(s4.x, c4.x));
+                    im.y = fadd(im.y, fmul(s4.y, c4.y));
+                    im.z = fadd(im.z, fmul(s4.z, c4.z));
+                    im.w = fadd(im.w, fmul(s4.w, c4.w));
+                    st4(ip, im);
+                }
+                if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
+                    float *ip = a.img + (long long)(gi - a.img_gi0) * pitch + j0;
+                    const float4 s4 = ld4_stream(a.img_field + (long long)lr * pitch + j0);
+                    float4 im = ld4(ip);
+                    im.x = fadd(im.x, fmul(s4.x, res[0]));
+                    im.y = fadd(im.y, fmul(s4.y, res[1]));
+                    im.z = fadd(im.z, fmul(s4.z, res[2]));
+                    im.w = fadd(im.w, fmul(s4.w, res[3]));
+                    st4(ip, im);
+                }
+                pc += pitch;
+                ppc += pitch;
+                vc += pitch;
+            }
+        }
+    }
+}
+
+/* stand-alone Laplacian (config 1; kernel_lap fd-source-code.cu:110-135): the
+ * exact reference sequence including the leading "0 +" adds; ring written 0. */
+template <int ORDER>
+FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, int bdim)
+{
+    constexpr int H = ORDER / 2, W = ORDER + 1;
+    const int q = bx * bdim + tid;
+    if (q >= a.ncol4) return;
+    const int j0 = q * 4;
+    const int rb = a.row0 + by * a.rows_per_cta;
+    const int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
+    if (rb >= re) return;
+    const long long pitch = a.pitch;
+    unsigned mlap = 0;
+    FDW_UNROLL
+    for (int k = 0; k < 4; k++)
+        if (j0 + k >= a.lap_j0 && j0 + k < a.lap_j1) mlap |= 1u << k;
+    const float *pc = a.p + j0 + (long long)(rb - H) * pitch;
+    float *out = lap + j0 + (long long)rb * pitch;
+    float4 w[W];
+    FDW_UNROLL
+    for (int s = 0; s < 2 * H; s++) {
+        w[s] = ld4(pc);
+        pc += pitch;
+    }
+    for (int r = rb; r < re; r += W) {
+        FDW_UNROLL
+        for (int u = 0; u < W; u++) {
+            const int lr = r + u;
+            if (lr < re) {
+                const int gi = a.grow0 + lr;
+                w[(u + 2 * H) % W] = ld4(pc);
+                const float *ctr = pc - (long long)H * pitch;
+                const float4 l4 = ld4(ctr - 4), r4 = ld4(ctr + 4), c4 = w[(u + H) % W];
+                const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
+                const unsigned ml = (gi >= a.lap_i0 && gi < a.lap_i1) ? mlap : 0u;
+                float res[4];
+                FDW_UNROLL
+                for (int k = 0; k < 4; k++) {
+                    float az = 0.0f, ax = 0.0f;
+                    FDW_UNROLL
+                    for (int io = 0; io <= ORDER; io++) {
+                        az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
+                        ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
+                    }
+                    res[k] = ((ml >> k) & 1u) ? fadd(az, ax) : 0.0f;
+                }
+                st4(out, make_float4(res[0], res[1], res[2], res[3]));
+                pc += pitch;
+                out += pitch;
+            }
+        }
+    }
+}
+
+} /* namespace fdw */
+#endif

@@ -1,0 +1,64 @@
+/*
+ * emu_cuda.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A host stand-in for the handful of CUDA runtime calls libfdwave makes, so
+ * that the library's HOST logic (context set-up, sponge bookkeeping, launch
+ * geometry, epilogue arguments, pipelines) and the per-thread kernel bodies
+ * (fdw_step_core.h compiles for the host) can be unit-tested on a machine
+ * without a GPU (`pytest -m "not gpu"`).  It builds tests/emu/libfdwave_emu.so;
+ * the product package never loads that file -- parallel_finite_difference_
+ * computation_b200/_lib.py loads libfdwave.so only and fails loudly when a
+ * CUDA device is missing.  Device allocations are poisoned with NaNs to catch
+ * reliance on zero-initialised memory.
+ */
+#ifndef EMU_CUDA_H
+#define EMU_CUDA_H
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1 };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct uint3_emu { unsigned x, y, z; };
+extern thread_local uint3_emu blockIdx, threadIdx;
+extern thread_local dim3 blockDim, gridDim;
+struct cudaDeviceProp { int multiProcessorCount; };
+
+#define __global__
+#define __grid_constant__
+#define __launch_bounds__(...)
+
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+
+cudaError_t cudaSetDevice(int);
+cudaError_t cudaGetDeviceCount(int *);
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp *, int);
+const char *cudaGetErrorString(cudaError_t);
+cudaError_t cudaGetLastError(void);
+cudaError_t cudaMalloc(void **, size_t);
+template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
+cudaError_t cudaFree(void *);
+cudaError_t cudaMemsetAsync(void *, int, size_t, cudaStream_t);
+cudaError_t cudaMemcpyAsync(void *, const void *, size_t, cudaMemcpyKind, cudaStream_t);
+cudaError_t cudaMemcpy2DAsync(void *, size_t, const void *, size_t, size_t, size_t, cudaMemcpyKind, cudaStream_t);
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
+cudaError_t cudaStreamSynchronize(cudaStream_t);
+cudaError_t cudaStreamDestroy(cudaStream_t);
+cudaError_t cudaEventCreate(cudaEvent_t *);
+cudaError_t cudaEventDestroy(cudaEvent_t);
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t);
+cudaError_t cudaEventSynchronize(cudaEvent_t);
+cudaError_t cudaEventElapsedTime(float *, cudaEvent_t, cudaEvent_t);
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *, const void *, int, size_t);
+/* `func` is a thunk void(*)(void **args) executed once per emulated thread */
+cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t);
+#endif

@@ -1,0 +1,73 @@
+"""CPU-only: libfdwave's host logic and kernel bodies (host build against the
+fake CUDA runtime in tests/emu/) vs the oracle.  The GPU tests run the same
+cases through the real library (test_gpu_parity.py)."""
+import pytest
+
+import parity_cases as PC
+from emu_loader import load as load_emu
+from parallel_finite_difference_computation_b200 import (FAMILY_CPU, FAMILY_GPU, RECIPE_C, RECIPE_FAST, RECIPE_G,
+                                                         SRC_GAUSS7, SRC_POINT, TAPER_FOUR, TAPER_NONE, TAPER_TOP)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
+
+
+@pytest.mark.parametrize("order", [2, 4, 6, 8])
+@pytest.mark.parametrize("shape", [(61, 47), (40, 64), (9, 9), (300, 130)])
+def test_stencil(emu, order, shape):
+    PC.case_stencil(emu, order, shape)
+
+
+def test_stencil_golden(emu, golden_dir):
+    PC.case_stencil_golden(emu, golden_dir)
+
+
+@pytest.mark.parametrize("order", [2, 4, 6, 8])
+@pytest.mark.parametrize("family,recipe,taper,src", [
+    (FAMILY_GPU, RECIPE_G, TAPER_TOP, SRC_POINT),
+    (FAMILY_GPU, RECIPE_G, TAPER_NONE, SRC_POINT),
+    (FAMILY_CPU, RECIPE_C, TAPER_TOP, SRC_POINT),
+    (FAMILY_CPU, RECIPE_C, TAPER_FOUR, SRC_GAUSS7),
+])
+def test_advance_bit_exact(emu, order, family, recipe, taper, src):
+    PC.case_advance(emu, family, recipe, taper, order=order, src_kind=src)
+
+
+@pytest.mark.parametrize("family,recipe,taper", [(FAMILY_GPU, RECIPE_G, TAPER_TOP), (FAMILY_CPU, RECIPE_C, TAPER_FOUR),
+                                                 (FAMILY_CPU, RECIPE_C, TAPER_TOP)])
+def test_advance_nonzero_initial_fields(emu, family, recipe, taper):
+    PC.case_advance(emu, family, recipe, taper, random_init=True, nt=7)
+
+
+@pytest.mark.parametrize("dims", [(37, 29, 9, 8), (50, 43, 16, 16), (41, 35, 11, 13)])
+def test_advance_compat_extents(emu, dims):
+    nx, nz, nxb, nzb = dims
+    PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=nx, nz=nz, nxb=nxb, nzb=nzb, compat=True)
+    PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=nx, nz=nz, nxb=nxb, nzb=nzb, compat=True,
+                    random_init=True, nt=5)
+
+
+def test_advance_wide_grid_many_chunks(emu):
+    PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=90, nz=1100, nxb=10, nzb=12, nt=6)
+
+
+def test_fast_recipe_within_tolerance(emu):
+    PC.case_advance(emu, FAMILY_GPU, RECIPE_FAST, TAPER_TOP, nt=60, tol=5e-5)
+
+
+@pytest.mark.parametrize("compat", [True, False])
+@pytest.mark.parametrize("roundtrip", [True, False])
+def test_gpu_family_rtm_shot(emu, compat, roundtrip):
+    PC.case_gpu_rtm(emu, compat=compat, host_roundtrip=roundtrip)
+
+
+def test_mod_main_shot(emu):
+    PC.case_mod_shot(emu)
+    PC.case_mod_shot(emu, order=4, nx=30, nz=41, nxb=5, nzb=9)
+
+
+@pytest.mark.parametrize("is_", [0, 1])
+def test_rtm_main_shot(emu, is_):
+    PC.case_rtm_shot_cpu(emu, is_=is_)
