@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the propagation hot path.
+
+Metric (BASELINE.json): grid-point updates/s (Gpts/s) of the fused
+Laplacian+leapfrog propagator, plus achieved HBM GB/s against the measured
+B200 roofline.
+
+Workload (BASELINE.json configs[2]): synthetic 2-D
+propagator on a 16384 x 16384 extended grid (40-point sponge inside it),
+order 8, dx=dz=10 m, dt=1 ms, 3-layer velocity 2000/3000/4000 m/s, point
+source, top sponge, GPU-family arithmetic (recipe G, bit-exact with the
+reference's kernel_lap + kernel_time).  One bench "step" = LEVELS time levels
+of that grid (the full job of 10k time levels = 10000/LEVELS steps).  With N
+GPUs the grid is slab-decomposed along x with a per-level halo exchange and
+the per-GPU slab stays 16384 x 16384 (weak scaling).
+
+    python bench.py --gpus 1 --steps K --warmup W          # our arm
+    python bench.py --impl reference --steps K --warmup W  # reference CPU path
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NGRID = int(os.environ.get("FDW_BENCH_N", "16384"))
+LEVELS = int(os.environ.get("FDW_BENCH_LEVELS", "250"))
+NB = 40
+DX = DZ = 10.0
+DT = 0.001
+FPEAK = 20.0
+FAC = 0.75
+BYTES_PER_POINT = 16  # read p, pp, v2*dt2 + write pp
+METRIC = "grid-point updates/sec"
+UNIT = "Gpts/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def layered_v2(nxe, nze):
+    ve = np.empty((nxe, nze), np.float32)
+    ve[:, : nze // 3] = 2000.0
+    ve[:, nze // 3: 2 * nze // 3] = 3000.0
+    ve[:, 2 * nze // 3:] = 4000.0
+    return ve * ve
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------- reference arm
+def reference_steps(nsteps, warmup, sample_n, sample_levels):
+    """The reference's own CPU implementation of the path (oracle/_ref: fd_step +
+    point source + taper_apply2, i.e. rtm_main's forward loop, rtm_main.cpp:166-176),
+    serial like the reference; falls back to the oracle port with all cores."""
+    from oracle import oracle as O
+    from oracle import ref as R
+    nb = NB
+    n = sample_n
+    nx = nz = n - 2 * nb
+    v2 = layered_v2(n, n)
+    srce = O.ricker_wavelet(10000, DT, FPEAK, O.FAM_C)
+    rng = np.random.default_rng(1)
+    p = rng.standard_normal((n, n), dtype=np.float32)
+    pp = rng.standard_normal((n, n), dtype=np.float32)
+    sx, sz = n // 2, nb
+    times = []
+    if R.available("libref_cpufam.so"):
+        kind, cores = "reference", 1
+        cpu = R.CpuFam()
+        cpu.fd_init(8, n, n, DX, DZ, DT)
+        cpu.taper_init(nb, nb, FAC)
+
+        def level(it, p, pp):
+            cpu.fd_step(8, p, pp, v2)
+            pp[sx, sz] += srce[it]
+            cpu.taper_apply2(pp, nx, nz, nb, nb)
+            cpu.taper_apply2(p, nx, nz, nb, nb)
+    else:
+        kind, cores = "port", O.max_threads()
+        O.set_threads(cores)
+        lap = np.zeros_like(p)
+        tx, tz = O.taper_table(nb, FAC, O.FAM_C), O.taper_table(nb, FAC, O.FAM_C)
+
+        def level(it, p, pp):
+            O.fd_step(8, p, pp, v2, lap, DX, DZ, DT)
+            pp[sx, sz] += srce[it]
+            O.taper_top(pp, nb, tx, tz)
+            O.taper_top(p, nb, tx, tz)
+    it = 0
+    for s in range(warmup + nsteps):
+        t0 = time.perf_counter()
+        for _ in range(sample_levels):
+            level(it, p, pp)
+            p, pp = pp, p
+            it += 1
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    pts = float(n) * n * sample_levels
+    return pts * len(times) / sum(times) / 1e9, sum(times) / len(times), kind, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, lv = 2048, 2
+    value, t_step, kind, cores = reference_steps(args.steps, args.warmup, n, lv)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d levels of a %dx%d sub-grid of the workload per step "
+                                   "(fd_step + point source + taper_apply2, serial as shipped)" % (lv, n, n)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(ngpus):
+    return {"workload": "synthetic 2D stencil propagator, %dx%d extended grid per GPU (x extent %d over %d slab%s), "
+                        "order 8, recipe G (bit-exact), top sponge, point source; %d time levels per step"
+                        % (NGRID, NGRID, NGRID * ngpus, ngpus, "s" if ngpus > 1 else "", LEVELS),
+            "grid": [NGRID * ngpus, NGRID], "levels_per_step": LEVELS, "order": 8, "recipe": "G",
+            "partition": "slab-x%d" % ngpus if ngpus > 1 else "single",
+            "l2": "working set 3 GiB per GPU > 126 MB L2, no flush needed"}
+
+
+# ---------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+
+    import parallel_finite_difference_computation_b200 as fdw
+    from parallel_finite_difference_computation_b200 import distributed as fdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nxe_g, nze = NGRID * world, NGRID
+    nb = NB
+    nx, nz = nxe_g - 2 * nb, nze - 2 * nb
+    srce = fdw.host.ricker_wavelet(10000, DT, FPEAK, fdw.FAMILY_GPU)
+    prop = fdist.SlabPropagator(nx, nz, nb, nb, DX, DZ, DT, order=8, fac=FAC, family=fdw.FAMILY_GPU,
+                                taper=fdw.TAPER_TOP, device=local_rank, rank=rank, world=world)
+    stream = torch.cuda.current_stream()
+    prop.set_stream(stream.cuda_stream)
+    x0, x1 = prop.slab
+    v2_local = layered_v2(x1 - x0, nze)
+    prop.set_v2_local(v2_local)
+    prop.set_wavelet(srce)
+    prop.set_source(nxe_g // 2, nb)
+    prop.zero()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps of LEVELS levels
+    it = 0
+    for _ in range(args.warmup):
+        prop.advance(it, LEVELS)
+        it += LEVELS
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = prop.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        prop.advance(it, LEVELS)
+        it += LEVELS
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.result()
+    launches = prop.launch_count() - l0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    pts_per_step = float(nxe_g) * nze * LEVELS
+    value = pts_per_step * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- end to end: host (pinned) fields in, LEVELS levels, host fields out, through the C ABI
+    nloc = x1 - x0
+    hn = torch.zeros((nloc, nze), dtype=torch.float32).pin_memory()
+    ho = torch.zeros((nloc, nze), dtype=torch.float32).pin_memory()
+    hn_np, ho_np = hn.numpy(), ho.numpy()
+    e2e_steps = max(2, min(args.steps, 4))
+    prop.propagate_local(hn_np, ho_np, 0, LEVELS)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        prop.propagate_local(hn_np, ho_np, s * LEVELS, LEVELS)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = pts_per_step * e2e_steps / e2e_s / 1e9
+    field_bytes = nloc * nze * 4
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (one launch per level per GPU)
+    peak, peak_src = peaks()
+    per_launch_ms = ms / (args.steps * LEVELS)
+    launch_bytes = float(NGRID) * nze * BYTES_PER_POINT
+    achieved = launch_bytes / (per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("step_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, _, kind, cores = reference_steps(6, 1, 2048, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "6 time levels of a 2048x2048 sub-grid of the workload "
+                         "(reference fd_step + point source + taper_apply2, serial as shipped)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * field_bytes * world,
+                "d2h_bytes_per_step": 2 * field_bytes * world, "steps": e2e_steps,
+                "note": "fdw_propagate per step: both time levels H2D from pinned host memory, %d levels, both levels D2H" % LEVELS},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "k_step<8,G> fused Laplacian+leapfrog+sponge+source",
+                     "algorithmic_bytes_per_launch": launch_bytes, "avg_launch_ms": per_launch_ms},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -162,6 +162,32 @@ int fdw_rtm_shot_cpu(fdw_ctx *ctx, int sx, int sz, int gz, const float *dobs_all
  * [nxe][nze] host array, ring of width order/2 = 0. */
 int fdw_stencil(int order, int nxe, int nze, float dx, float dz, const float *in, float *out, int device);
 
+/* ---------------------------------------------------------------- slab decomposition
+ * A context created with slab_x0 < slab_x1 owns those rows of the extended
+ * grid plus GUARD ghost rows on each side.  One time level is then driven in
+ * three phases so that the caller can overlap the halo exchange with the
+ * interior update (the reference has no multi-GPU path; per-point arithmetic
+ * is unchanged, so N slabs reproduce the 1-GPU result bit for bit):
+ *   fdw_step_begin(it)            bookkeeping, builds the launch arguments
+ *   fdw_step_rows(r0, r1, stream) update local rows [r0,r1) (any number of calls)
+ *   fdw_step_end()                swaps the levels
+ * fdw_halo_get returns, for the level being written (level=1, between begin and
+ * end) or the newest level (level=0), the device addresses of the 4 boundary
+ * row blocks (GUARD rows x pitch floats each, contiguous). */
+typedef struct fdw_halo {
+    void *send_lo, *send_hi; /* first / last GUARD owned rows */
+    void *recv_lo, *recv_hi; /* ghost rows below row 0 / above row nloc-1 */
+    long long count;         /* floats per block */
+} fdw_halo;
+int fdw_step_begin(fdw_ctx *ctx, int it);
+int fdw_step_rows(fdw_ctx *ctx, int row0, int row1, void *cuda_stream);
+int fdw_step_end(fdw_ctx *ctx);
+int fdw_halo_get(fdw_ctx *ctx, int level, fdw_halo *out);
+/* slab-local host I/O: arrays hold only the owned rows, [nloc][nze] */
+int fdw_set_v2_local(fdw_ctx *ctx, const float *v2_rows);
+int fdw_fields_upload_local(fdw_ctx *ctx, int pair, const float *newest, const float *older);
+int fdw_fields_download_local(fdw_ctx *ctx, int pair, float *newest, float *older);
+
 /* ---------------------------------------------------------------- device-resident access
  * (benchmarks / multi-GPU plumbing; pointers are CUDA device pointers) */
 typedef struct fdw_devinfo {

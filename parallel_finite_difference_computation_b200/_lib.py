@@ -45,6 +45,11 @@ class Input(C.Structure):
                 ("has_datfile", C.c_int), ("has_vel_ext_file", C.c_int)]
 
 
+class Halo(C.Structure):
+    _fields_ = [("send_lo", C.c_void_p), ("send_hi", C.c_void_p), ("recv_lo", C.c_void_p), ("recv_hi", C.c_void_p),
+                ("count", C.c_longlong)]
+
+
 class DevInfo(C.Structure):
     _fields_ = [("newest", C.c_void_p), ("older", C.c_void_p), ("vdt", C.c_void_p), ("pitch", C.c_longlong),
                 ("nloc", C.c_int), ("gx0", C.c_int), ("nxe", C.c_int), ("nze", C.c_int), ("guard", C.c_int)]
@@ -81,6 +86,13 @@ SIGNATURES = {
     "fdw_model_shot": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p]),
     "fdw_rtm_shot_cpu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p]),
     "fdw_stencil": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, f32p, C.c_int]),
+    "fdw_step_begin": (C.c_int, [C.c_void_p, C.c_int]),
+    "fdw_step_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "fdw_step_end": (C.c_int, [C.c_void_p]),
+    "fdw_halo_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Halo)]),
+    "fdw_set_v2_local": (C.c_int, [C.c_void_p, f32p]),
+    "fdw_fields_upload_local": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p]),
+    "fdw_fields_download_local": (C.c_int, [C.c_void_p, C.c_int, _optf32, _optf32]),
     "fdw_devinfo_get": (C.c_int, [C.c_void_p, C.POINTER(DevInfo)]),
     "fdw_mark_begin": (C.c_int, [C.c_void_p]),
     "fdw_mark_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

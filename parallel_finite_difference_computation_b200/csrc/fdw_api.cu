@@ -91,6 +91,10 @@ struct fdw_ctx {
     int nsm = 0;
     bool saved_valid = false;
     int rows_per_cta_override = 0, threads_override = 0;
+    /* split-phase step (slab decomposition) */
+    bool step_open = false;
+    StepArgs step_args;
+    const void *step_kern = nullptr;
 };
 
 static int bind(fdw_ctx *c)
@@ -271,6 +275,22 @@ static int step_pair(fdw_ctx *c, int pair, int recipe, int epi, bool sponge, boo
     int t = c->newest[pair];
     c->newest[pair] = c->older[pair];
     c->older[pair] = t;
+    return FDW_OK;
+}
+
+static int launch_step_rows(fdw_ctx *c, const void *k, StepArgs a, int row0, int row1, cudaStream_t st)
+{
+    if (row0 < a.row0) row0 = a.row0;
+    if (row1 > a.row1) row1 = a.row1;
+    if (row1 <= row0 || a.ncol4 <= 0) return FDW_OK;
+    a.row0 = row0;
+    a.row1 = row1;
+    dim3 grid, block;
+    launch_geometry(k, c->nsm, a.ncol4, row1 - row0, c->threads_override, c->rows_per_cta_override, &grid, &block,
+                    &a.rows_per_cta);
+    void *params[] = {&a};
+    CU(cudaLaunchKernel(k, grid, block, params, 0, st));
+    c->launches++;
     return FDW_OK;
 }
 
@@ -792,6 +812,111 @@ extern "C" int fdw_stencil(int order, int nxe, int nze, float dx, float dz, cons
     }
     fdw_destroy(c);
     return rc;
+}
+
+/* ------------------------------------------------------------------ slab decomposition */
+extern "C" int fdw_step_begin(fdw_ctx *c, int it)
+{
+    if (!c) return FDW_ERR_ARG;
+    if (c->step_open) { fdw_set_error("fdw_step_begin: previous step not ended"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    Field &n = c->f[c->newest[0]], &o = c->f[c->older[0]];
+    const bool tap = c->prm.taper != FDW_TAPER_NONE;
+    if (tap && c->prm.family == FDW_FAMILY_GPU) { n.pend++; o.pend++; }
+    base_args(c, 0, &c->step_args);
+    c->step_args.taper_on = (n.pend || o.pend) ? 1 : 0;
+    if (!c->wavelet.empty()) set_source_args(c, &c->step_args, it);
+    c->step_kern = step_kernel(c->prm.order, c->prm.recipe, 0);
+    if (!c->step_kern) { fdw_set_error("fdw_step_begin: no kernel"); return FDW_ERR_UNSUPPORTED; }
+    c->step_open = true;
+    return FDW_OK;
+}
+
+extern "C" int fdw_step_rows(fdw_ctx *c, int row0, int row1, void *stream)
+{
+    if (!c) return FDW_ERR_ARG;
+    if (!c->step_open) { fdw_set_error("fdw_step_rows: no open step"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    return launch_step_rows(c, c->step_kern, c->step_args, row0, row1, stream ? (cudaStream_t)stream : c->stream);
+}
+
+extern "C" int fdw_step_end(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    if (!c->step_open) { fdw_set_error("fdw_step_end: no open step"); return FDW_ERR_STATE; }
+    Field &n = c->f[c->newest[0]], &o = c->f[c->older[0]];
+    o.pend = 0;
+    if (c->prm.taper != FDW_TAPER_NONE && c->prm.family == FDW_FAMILY_CPU) { o.pend = 1; n.pend++; }
+    int t = c->newest[0];
+    c->newest[0] = c->older[0];
+    c->older[0] = t;
+    c->step_open = false;
+    return FDW_OK;
+}
+
+extern "C" int fdw_halo_get(fdw_ctx *c, int level, fdw_halo *h)
+{
+    if (!c || !h || level < 0 || level > 1) return FDW_ERR_ARG;
+    if (level == 1 && !c->step_open) { fdw_set_error("fdw_halo_get(level=1) outside a step"); return FDW_ERR_STATE; }
+    /* level 1: the level being written = the "older" buffer of the open step */
+    float *r0 = c->f[level == 1 ? c->older[0] : c->newest[0]].r0;
+    h->send_lo = r0;
+    h->send_hi = r0 + (long long)(c->nloc - GUARD) * c->pitch;
+    h->recv_lo = r0 - (long long)GUARD * c->pitch;
+    h->recv_hi = r0 + (long long)c->nloc * c->pitch;
+    h->count = (long long)GUARD * c->pitch;
+    return FDW_OK;
+}
+
+static int rows_h2d(fdw_ctx *c, float *r0, const float *host)
+{
+    CU(cudaMemcpy2DAsync(r0, c->pitch * sizeof(float), host, (size_t)c->nze * sizeof(float),
+                         (size_t)c->nze * sizeof(float), c->nloc, cudaMemcpyHostToDevice, c->stream));
+    return FDW_OK;
+}
+
+static int rows_d2h(fdw_ctx *c, const float *r0, float *host)
+{
+    CU(cudaMemcpy2DAsync(host, (size_t)c->nze * sizeof(float), r0, c->pitch * sizeof(float),
+                         (size_t)c->nze * sizeof(float), c->nloc, cudaMemcpyDeviceToHost, c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_set_v2_local(fdw_ctx *c, const float *v2)
+{
+    if (!c || !v2) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CU(cudaMemsetAsync(c->vdt_base, 0, c->field_elems * sizeof(float), c->stream));
+    CHECK(rows_h2d(c, c->vdt, v2));
+    long long n = (long long)c->field_elems;
+    void *params[] = {&c->vdt_base, &n, &c->dt2};
+    CU(cudaLaunchKernel(FDW_KPTR(k_scale_rows, thunk_scale_rows), dim3((unsigned)((n + 255) / 256)), dim3(256), params,
+                        0, c->stream));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_fields_upload_local(fdw_ctx *c, int pair, const float *newest, const float *older)
+{
+    if (!c || pair < 0 || pair > 1 || !newest || !older) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    Field &n = c->f[c->newest[pair]], &o = c->f[c->older[pair]];
+    CHECK(rows_h2d(c, n.r0, newest));
+    CHECK(rows_h2d(c, o.r0, older));
+    n.pend = o.pend = 0;
+    return FDW_OK;
+}
+
+extern "C" int fdw_fields_download_local(fdw_ctx *c, int pair, float *newest, float *older)
+{
+    if (!c || pair < 0 || pair > 1) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    Field &n = c->f[c->newest[pair]], &o = c->f[c->older[pair]];
+    if (newest) { CHECK(materialize(c, n)); CHECK(rows_d2h(c, n.r0, newest)); }
+    if (older) { CHECK(materialize(c, o)); CHECK(rows_d2h(c, o.r0, older)); }
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
 }
 
 /* ------------------------------------------------------------------ device-resident access */

@@ -1,0 +1,215 @@
+"""Multi-GPU partitioning of the propagation path (one process per GPU).
+
+The reference has no multi-GPU code; both partitionings are
+new, and neither changes the per-point arithmetic:
+
+* slab decomposition (SlabPropagator): the extended grid is cut along x (the
+  slow axis, so a halo is GUARD contiguous rows) into `world` slabs.  Per time
+  level each rank (1) updates its two GUARD-row boundary strips, (2) starts the
+  exchange of those rows with its neighbours on a communication stream while
+  (3) the interior rows are updated on the compute stream, (4) joins.  An
+  N-slab run reproduces the single-domain result bit for bit.
+* shot parallelism (shot_partition / reduce_image): shots are independent
+  units; the only collective is the final image sum.
+
+`torch.distributed` (NCCL on GPUs, gloo in the CPU unit tests) is plumbing:
+rendezvous, the halo send/recv and the image reduction.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .propagator import Wave2D
+
+GUARD = 4
+
+
+def slab_rows(nxe, world, rank):
+    """contiguous, near-equal row blocks of the extended grid"""
+    x0 = (nxe * rank) // world
+    x1 = (nxe * (rank + 1)) // world
+    return x0, x1
+
+
+def shot_partition(ns, world, rank):
+    """shots handled by `rank` (round-robin keeps the load even when ns % world != 0)"""
+    return list(range(rank, ns, world))
+
+
+class _CudaView:
+    """minimal __cuda_array_interface__ carrier so torch can alias library-owned device memory"""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class SlabPropagator:
+    """Wave2D over one slab of a slab-decomposed grid (world == 1: the whole grid)."""
+
+    def __init__(self, nx, nz, nxb, nzb, dx, dz, dt, rank=0, world=1, device=0, lib=None, on_gpu=True, **kw):
+        self.rank, self.world, self.on_gpu = rank, world, on_gpu
+        self.nxe, self.nze = nx + 2 * nxb, nz + 2 * nzb
+        self.slab = slab_rows(self.nxe, world, rank)
+        self.nloc = self.slab[1] - self.slab[0]
+        if world > 1 and self.nloc < 2 * GUARD:
+            raise ValueError("slab of %d rows is thinner than two halos" % self.nloc)
+        self.w = Wave2D(nx, nz, nxb, nzb, dx, dz, dt, device=device, slab=self.slab if world > 1 else None,
+                        lib=lib, **kw)
+        self.L, self.h = self.w.L, self.w.h
+        self._views = {}
+        self._compute_stream = None
+        self._comm_stream = None
+        self._event = None
+        if world > 1 and on_gpu:
+            import torch
+            self._comm_stream = torch.cuda.Stream(priority=-1)
+            self._event = torch.cuda.Event()
+
+    # -- plumbing
+    def close(self):
+        self.w.close()
+
+    def set_stream(self, cuda_stream):
+        self.w.set_stream(cuda_stream)
+        self._compute_stream = cuda_stream
+
+    def set_wavelet(self, s):
+        self.w.set_wavelet(s)
+
+    def set_source(self, sx, sz, kind=_lib.SRC_POINT):
+        self.w.set_source(sx, sz, kind)
+
+    def zero(self):
+        self.w.zero()
+
+    def launch_count(self):
+        return self.w.launch_count()
+
+    def set_v2_local(self, v2_rows):
+        v2_rows = np.ascontiguousarray(v2_rows, np.float32)
+        assert v2_rows.shape == (self.nloc, self.nze)
+        _lib.check(self.L, self.L.fdw_set_v2_local(self.h, v2_rows))
+
+    def upload_local(self, newest, older):
+        _lib.check(self.L, self.L.fdw_fields_upload_local(self.h, 0, newest, older))
+        self.refresh_halos()
+
+    def download_local(self, newest=None, older=None):
+        n = np.zeros((self.nloc, self.nze), np.float32) if newest is None else newest
+        o = np.zeros((self.nloc, self.nze), np.float32) if older is None else older
+        _lib.check(self.L, self.L.fdw_fields_download_local(
+            self.h, 0, n.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p)))
+        return n, o
+
+    # -- halo exchange
+    def _tensor(self, ptr, count):
+        key = (ptr, count)
+        t = self._views.get(key)
+        if t is None:
+            import torch
+            if self.on_gpu:
+                t = torch.as_tensor(_CudaView(ptr, count), device="cuda")
+            else:
+                buf = (C.c_float * count).from_address(ptr)
+                t = torch.from_numpy(np.ctypeslib.as_array(buf))
+            self._views[key] = t
+        return t
+
+    def _exchange_ops(self, level):
+        import torch.distributed as dist
+        hl = _lib.Halo()
+        _lib.check(self.L, self.L.fdw_halo_get(self.h, level, C.byref(hl)))
+        n = hl.count
+        ops = []
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, self._tensor(hl.send_lo, n), self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, self._tensor(hl.recv_lo, n), self.rank - 1))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.isend, self._tensor(hl.send_hi, n), self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, self._tensor(hl.recv_hi, n), self.rank + 1))
+        return ops
+
+    def refresh_halos(self):
+        """exchange the boundary rows of the newest level (after an upload)"""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        if self.on_gpu:
+            self.w.sync()
+        for r in dist.batch_isend_irecv(self._exchange_ops(0)):
+            r.wait()
+        if self.on_gpu:
+            import torch
+            torch.cuda.current_stream().synchronize()
+
+    # -- time stepping
+    def advance(self, it0, nsteps):
+        if self.world == 1:
+            self.w.advance(it0, nsteps)
+            return
+        import torch.distributed as dist
+        L, h = self.L, self.h
+        lo_nb, hi_nb = self.rank > 0, self.rank < self.world - 1
+        ilo = GUARD if lo_nb else 0
+        ihi = self.nloc - GUARD if hi_nb else self.nloc
+        if self.on_gpu:
+            import torch
+            compute = torch.cuda.current_stream()
+            cs = C.c_void_p(compute.cuda_stream)
+        else:
+            cs = None
+        for it in range(it0, it0 + nsteps):
+            _lib.check(L, L.fdw_step_begin(h, it))
+            if lo_nb:
+                _lib.check(L, L.fdw_step_rows(h, 0, GUARD, cs))
+            if hi_nb:
+                _lib.check(L, L.fdw_step_rows(h, self.nloc - GUARD, self.nloc, cs))
+            ops = self._exchange_ops(1)
+            if self.on_gpu:
+                self._event.record(compute)
+                self._comm_stream.wait_event(self._event)
+                with torch.cuda.stream(self._comm_stream):
+                    reqs = dist.batch_isend_irecv(ops)
+                _lib.check(L, L.fdw_step_rows(h, ilo, ihi, cs))  # interior overlaps the exchange
+                with torch.cuda.stream(self._comm_stream):
+                    for r in reqs:
+                        r.wait()
+                    self._event.record(self._comm_stream)
+                compute.wait_event(self._event)
+            else:
+                reqs = dist.batch_isend_irecv(ops)
+                _lib.check(L, L.fdw_step_rows(h, ilo, ihi, cs))
+                for r in reqs:
+                    r.wait()
+            _lib.check(L, L.fdw_step_end(h))
+
+    def propagate_local(self, newest, older, it0, nsteps):
+        """slab-local host rows in, nsteps levels, host rows out (in place)"""
+        if self.world == 1:
+            self.w.propagate(newest, older, it0, nsteps)
+            return
+        self.upload_local(newest, older)
+        self.advance(it0, nsteps)
+        self.download_local(newest, older)
+
+
+def reduce_image(img, op="ordered"):
+    """stack per-rank partial images (img += imloc of fd-code.cu:525 / rtm_main.cpp:237).
+    'ordered' gathers to every rank and sums in rank order (bit-reproducible);
+    'allreduce' is a single NCCL/gloo all-reduce (fast path, order unspecified)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return img
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(np.ascontiguousarray(img, np.float32)).to(dev)
+    if op == "allreduce":
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t)
+    acc = parts[0].clone()
+    for q in parts[1:]:
+        acc += q
+    return acc.cpu().numpy()
