@@ -209,7 +209,9 @@ def run_ours(args):
     srce = fdw.host.ricker_wavelet(10000, DT, FPEAK, fdw.FAMILY_GPU)
     prop = fdist.SlabPropagator(nx, nz, nb, nb, DX, DZ, DT, order=8, fac=FAC, family=fdw.FAMILY_GPU,
                                 taper=fdw.TAPER_TOP, device=local_rank, rank=rank, world=world)
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: the library launches on it, and the torch events below time it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     prop.set_stream(stream.cuda_stream)
     x0, x1 = prop.slab
     v2_local = layered_v2(x1 - x0, nze)

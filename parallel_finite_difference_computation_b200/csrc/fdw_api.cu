@@ -86,7 +86,8 @@ struct fdw_ctx {
     size_t dobs_cap = 0, rec_cap = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side = nullptr;
     long long launches = 0;
     int nsm = 0;
     bool saved_valid = false;
@@ -138,13 +139,13 @@ static void thunk_materialize(void **a)
 #endif
 
 /* ------------------------------------------------------------------ helpers */
-static const void *step_kernel(int order, int recipe, int epi)
+static const void *step_kernel(int order, int recipe, int epi, int sponge)
 {
     switch (order) {
-    case 2: return fdw_step_kernel_o2(recipe, epi);
-    case 4: return fdw_step_kernel_o4(recipe, epi);
-    case 6: return fdw_step_kernel_o6(recipe, epi);
-    case 8: return fdw_step_kernel_o8(recipe, epi);
+    case 2: return fdw_step_kernel_o2(recipe, epi, sponge);
+    case 4: return fdw_step_kernel_o4(recipe, epi, sponge);
+    case 6: return fdw_step_kernel_o6(recipe, epi, sponge);
+    case 8: return fdw_step_kernel_o8(recipe, epi, sponge);
     }
     return nullptr;
 }
@@ -163,29 +164,25 @@ static const void *lap_kernel(int order)
 static long long pitch_for(int nze) { return ((long long)nze + 4 + 31) / 32 * 32; }
 
 /* launch geometry: one thread per float4 column, CTAs of up to 256 threads
- * tiling z; x is cut into chunks so that the grid is a whole number of waves
- * of (SM count x resident CTAs). */
-static void launch_geometry(const void *kern, int nsm, int ncol4, int rows, int thr_override, int rpc_override,
+ * tiling z; x is cut into chunks of rows_per_cta rows.  Measured on B200
+ * (tools/kbench.cu): short chunks (16-32 rows) win -- the 8 halo rows a chunk
+ * re-reads hit L2, while many small CTAs remove the wave-quantisation tail. */
+static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int thr_override, int rpc_override,
                             dim3 *grid, dim3 *block, int *rows_per_cta)
 {
-    int nthreads = ncol4 >= 256 ? 256 : ((ncol4 + 31) / 32) * 32;
+    int nthreads = ncols >= 256 ? 256 : ((ncols + 31) / 32) * 32;
     if (thr_override > 0) nthreads = thr_override;
     if (nthreads < 32) nthreads = 32;
-    int gx = (ncol4 + nthreads - 1) / nthreads;
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, 0) != cudaSuccess || occ < 1) occ = 1;
-    long long cap = (long long)nsm * occ;
-    int rpc;
+    int gx = (ncols + nthreads - 1) / nthreads;
+    int rpc = 32;
     if (rpc_override > 0) {
         rpc = rpc_override;
     } else {
-        double waves = (double)gx * rows / ((double)cap * 96.0);
-        long long k = (long long)(waves + 0.5);
-        if (k < 1) k = 1;
-        long long gy = k * cap / gx;
-        if (gy < 1) gy = 1;
-        rpc = (int)((rows + gy - 1) / gy);
-        if (rpc < 8) rpc = 8;
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, 0) != cudaSuccess || occ < 1) occ = 1;
+        const long long cap = (long long)nsm * occ;
+        /* small problems: shorten the chunks until the grid fills the machine twice over */
+        while (rpc > 8 && (long long)gx * ((rows + rpc - 1) / rpc) < 2 * cap) rpc /= 2;
     }
     int gy = (rows + rpc - 1) / rpc;
     *grid = dim3(gx, gy < 1 ? 1 : gy, 1);
@@ -201,10 +198,10 @@ static void base_args(const fdw_ctx *c, int pair, StepArgs *a)
     a->pp = o.r0;
     a->vdt = c->vdt;
     a->pitch = c->pitch;
+    a->col4_0 = 0;
     a->ncol4 = c->ncol4;
     a->grow0 = c->gx0;
     a->lap_i0 = c->lap_i0; a->lap_i1 = c->lap_i1; a->lap_j0 = c->lap_j0; a->lap_j1 = c->lap_j1;
-    a->upd_j1 = c->upd_j1;
     a->nze = c->nze;
     memcpy(a->cz, c->cz, sizeof a->cz);
     memcpy(a->cx, c->cx, sizeof a->cx);
@@ -223,22 +220,72 @@ static void base_args(const fdw_ctx *c, int pair, StepArgs *a)
     a->row1 = hi < c->nloc ? (hi < 0 ? 0 : hi) : c->nloc;
 }
 
-static int launch_step(fdw_ctx *c, StepArgs *a, int recipe, int epi)
+/* One time level = one launch of the plain kernel on the sponge-free
+ * rectangle plus launches of the sponge kernel on the thin strips (columns)
+ * and row bands where some factor differs from 1.  The strips run on a side
+ * stream, forked from and joined to `st` with events, so they overlap the
+ * bulk launch instead of serialising behind it. */
+struct Rect { int c0, c1, r0, r1, sponge; };
+
+static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, const Rect &rc, cudaStream_t st)
 {
-    const void *k = step_kernel(c->prm.order, recipe, epi);
+    if (rc.c1 <= rc.c0 || rc.r1 <= rc.r0) return FDW_OK;
+    const void *k = step_kernel(c->prm.order, recipe, epi, rc.sponge);
     if (!k) {
         fdw_set_error("no kernel for order %d recipe %d epilogue %d", c->prm.order, recipe, epi);
         return FDW_ERR_UNSUPPORTED;
     }
-    int rows = a->row1 - a->row0;
-    if (rows <= 0 || a->ncol4 <= 0) return FDW_OK;
+    StepArgs a = base;
+    a.col4_0 = rc.c0; a.ncol4 = rc.c1; a.row0 = rc.r0; a.row1 = rc.r1;
     dim3 grid, block;
-    launch_geometry(k, c->nsm, a->ncol4, rows, c->threads_override, c->rows_per_cta_override, &grid, &block,
-                    &a->rows_per_cta);
-    void *params[] = {a};
-    CU(cudaLaunchKernel(k, grid, block, params, 0, c->stream));
+    launch_geometry(k, c->nsm, rc.c1 - rc.c0, rc.r1 - rc.r0, c->threads_override, c->rows_per_cta_override, &grid,
+                    &block, &a.rows_per_cta);
+    void *params[] = {&a};
+    CU(cudaLaunchKernel(k, grid, block, params, 0, st));
     c->launches++;
     return FDW_OK;
+}
+
+static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, int row0, int row1, cudaStream_t st)
+{
+    if (row0 < base.row0) row0 = base.row0;
+    if (row1 > base.row1) row1 = base.row1;
+    if (row1 <= row0 || base.ncol4 <= 0) return FDW_OK;
+    const int nc = base.ncol4, H = c->H;
+    if (!base.taper_on) {
+        Rect all = {0, nc, row0, row1, 0};
+        return launch_rect(c, base, recipe, epi, all, st);
+    }
+    /* columns whose own samples or z neighbours (+-4) sit in a z sponge, in whole warps */
+    int cs = 0, cb = nc;
+    if (c->tap_jlo > INT_MIN) cs = (((c->tap_jlo + 4 + 3) / 4) + 31) / 32 * 32;
+    if (c->tap_jhi < INT_MAX) cb = ((c->tap_jhi - 7 > 0 ? c->tap_jhi - 7 : 0) / 4) / 32 * 32;
+    if (cs > nc) cs = nc;
+    if (cb < cs) cb = cs;
+    /* rows whose x window touches an x sponge that applies to every column */
+    int rl = row0, rh = row1;
+    if (c->tap_ilo > INT_MIN) { int v = c->tap_ilo + H - c->gx0; rl = v < row0 ? row0 : (v > row1 ? row1 : v); }
+    if (c->tap_ihi < INT_MAX) { int v = c->tap_ihi - H - c->gx0; rh = v < rl ? rl : (v > row1 ? row1 : v); }
+    Rect sponge[4] = {{0, cs, row0, row1, 1}, {cb, nc, row0, row1, 1}, {cs, cb, row0, rl, 1}, {cs, cb, rh, row1, 1}};
+    Rect bulk = {cs, cb, rl, rh, 0};
+    const bool fork = bulk.c1 > bulk.c0 && bulk.r1 > bulk.r0;
+    cudaStream_t ss = fork ? c->side : st;
+    if (fork) {
+        CU(cudaEventRecord(c->ev_fork, st));
+        CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+    }
+    for (int k = 0; k < 4; k++) CHECK(launch_rect(c, base, recipe, epi, sponge[k], ss));
+    if (fork) {
+        CU(cudaEventRecord(c->ev_join, ss));
+        CHECK(launch_rect(c, base, recipe, epi, bulk, st));
+        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+    }
+    return FDW_OK;
+}
+
+static int launch_step(fdw_ctx *c, StepArgs *a, int recipe, int epi)
+{
+    return launch_level(c, *a, recipe, epi, a->row0, a->row1, c->stream);
 }
 
 static void set_source_args(const fdw_ctx *c, StepArgs *a, int it)
@@ -275,22 +322,6 @@ static int step_pair(fdw_ctx *c, int pair, int recipe, int epi, bool sponge, boo
     int t = c->newest[pair];
     c->newest[pair] = c->older[pair];
     c->older[pair] = t;
-    return FDW_OK;
-}
-
-static int launch_step_rows(fdw_ctx *c, const void *k, StepArgs a, int row0, int row1, cudaStream_t st)
-{
-    if (row0 < a.row0) row0 = a.row0;
-    if (row1 > a.row1) row1 = a.row1;
-    if (row1 <= row0 || a.ncol4 <= 0) return FDW_OK;
-    a.row0 = row0;
-    a.row1 = row1;
-    dim3 grid, block;
-    launch_geometry(k, c->nsm, a.ncol4, row1 - row0, c->threads_override, c->rows_per_cta_override, &grid, &block,
-                    &a.rows_per_cta);
-    void *params[] = {&a};
-    CU(cudaLaunchKernel(k, grid, block, params, 0, st));
-    c->launches++;
     return FDW_OK;
 }
 
@@ -478,8 +509,11 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     } while (0)
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     TRY(cudaEventCreate(&c->ev0));
     TRY(cudaEventCreate(&c->ev1));
+    TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int k = 0; k < 4; k++) {
         rc = field_alloc(c, &c->f[k]);
         if (rc != FDW_OK) { fdw_destroy(c); return rc; }
@@ -519,6 +553,9 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     cudaFree(c->hist); cudaFree(c->img); cudaFree(c->dobs_d); cudaFree(c->rec_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -774,6 +811,7 @@ static int launch_lap(fdw_ctx *c, const float *src, float *dst)
     StepArgs a;
     base_args(c, 0, &a);
     a.p = src;
+    a.col4_0 = 0;
     a.ncol4 = (c->nze + 3) / 4;
     a.row0 = 0;
     a.row1 = c->nloc;
@@ -826,8 +864,6 @@ extern "C" int fdw_step_begin(fdw_ctx *c, int it)
     base_args(c, 0, &c->step_args);
     c->step_args.taper_on = (n.pend || o.pend) ? 1 : 0;
     if (!c->wavelet.empty()) set_source_args(c, &c->step_args, it);
-    c->step_kern = step_kernel(c->prm.order, c->prm.recipe, 0);
-    if (!c->step_kern) { fdw_set_error("fdw_step_begin: no kernel"); return FDW_ERR_UNSUPPORTED; }
     c->step_open = true;
     return FDW_OK;
 }
@@ -837,7 +873,7 @@ extern "C" int fdw_step_rows(fdw_ctx *c, int row0, int row1, void *stream)
     if (!c) return FDW_ERR_ARG;
     if (!c->step_open) { fdw_set_error("fdw_step_rows: no open step"); return FDW_ERR_STATE; }
     CHECK(bind(c));
-    return launch_step_rows(c, c->step_kern, c->step_args, row0, row1, stream ? (cudaStream_t)stream : c->stream);
+    return launch_level(c, c->step_args, c->prm.recipe, 0, row0, row1, stream ? (cudaStream_t)stream : c->stream);
 }
 
 extern "C" int fdw_step_end(fdw_ctx *c)

@@ -9,10 +9,10 @@ extern "C" {
 void fdw_set_error(const char *fmt, ...);
 
 /* per-order kernel tables (fdw_kernels_o{2,4,6,8}.cu) */
-const void *fdw_step_kernel_o2(int recipe, int epi);
-const void *fdw_step_kernel_o4(int recipe, int epi);
-const void *fdw_step_kernel_o6(int recipe, int epi);
-const void *fdw_step_kernel_o8(int recipe, int epi);
+const void *fdw_step_kernel_o2(int recipe, int epi, int sponge);
+const void *fdw_step_kernel_o4(int recipe, int epi, int sponge);
+const void *fdw_step_kernel_o6(int recipe, int epi, int sponge);
+const void *fdw_step_kernel_o8(int recipe, int epi, int sponge);
 const void *fdw_lap_kernel_o2(void);
 const void *fdw_lap_kernel_o4(void);
 const void *fdw_lap_kernel_o6(void);

@@ -51,12 +51,12 @@ struct StepArgs {
     float *pp;       /* older level in, next level out (in place, own column only) */
     const float *vdt; /* fl32(v2*dt2), same layout */
     long long pitch; /* floats per row, multiple of 32, >= nze+4 */
-    int ncol4;       /* float4 columns that are updated */
+    int col4_0;      /* first float4 column of this launch */
+    int ncol4;       /* one past the last float4 column of this launch */
     int row0, row1;  /* local rows [row0,row1) handled by this launch */
     int rows_per_cta;
     int grow0;       /* global x index of local row 0 */
     int lap_i0, lap_i1, lap_j0, lap_j1; /* Laplacian is non-zero only inside (global) */
-    int upd_j1;      /* columns j < upd_j1 are updated (row extent is clamped by the host) */
     int nze;         /* valid columns per row */
     float cz[9], cx[9]; /* G/FAST: premultiplied weights; C: both hold the raw weights */
     float dz2inv, dx2inv;
@@ -136,23 +136,11 @@ FDW_HD float4 tap4(float4 v, const float *zf, unsigned xon, float xf, bool zon, 
     return make_float4(e[0], e[1], e[2], e[3]);
 }
 
-/* does this CTA touch a point whose sponge factor differs from 1 ? */
-FDW_HD bool block_needs_taper(const StepArgs &a, int bx, int by, int bdim, int half)
-{
-    if (!a.taper_on) return false;
-    int jlo = bx * bdim * 4 - 4, jhi = (bx + 1) * bdim * 4 + 4;
-    if (jlo < a.tap_jlo || jhi > a.tap_jhi) return true;
-    int rb = a.row0 + by * a.rows_per_cta;
-    int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
-    int glo = a.grow0 + rb - half, ghi = a.grow0 + re + half;
-    return glo < a.tap_ilo || ghi > a.tap_ihi;
-}
-
 template <int ORDER, int RECIPE, bool TAPER, int EPI>
 FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
 {
     constexpr int H = ORDER / 2, W = ORDER + 1;
-    const int q = bx * bdim + tid;
+    const int q = a.col4_0 + bx * bdim + tid;
     if (q >= a.ncol4) return;
     const int j0 = q * 4;
     const int rb = a.row0 + by * a.rows_per_cta;
@@ -161,12 +149,11 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
     const long long pitch = a.pitch;
 
     /* per-thread column predicates */
-    unsigned mlap = 0, mupd = 0;
+    unsigned mlap = 0;
     FDW_UNROLL
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 4; k++)
         if (j0 + k >= a.lap_j0 && j0 + k < a.lap_j1) mlap |= 1u << k;
-        if (j0 + k < a.upd_j1) mupd |= 1u << k;
-    }
+    const bool src_cols = a.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
 
     /* sponge factors of the 12 columns j0-4 .. j0+7 */
     float zf[12];
@@ -179,9 +166,9 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
         }
     }
 
-    const float *pc = a.p + j0 + (long long)(rb - H) * pitch; /* row being streamed in */
-    float *ppc = a.pp + j0 + (long long)rb * pitch;
-    const float *vc = a.vdt + j0 + (long long)rb * pitch;
+    const float *__restrict__ pc = a.p + j0 + (long long)(rb - H) * pitch; /* row being streamed in */
+    float *__restrict__ ppc = a.pp + j0 + (long long)rb * pitch;
+    const float *__restrict__ vc = a.vdt + j0 + (long long)rb * pitch;
 
     float4 w[W];
     FDW_UNROLL
@@ -264,8 +251,7 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                 }
 
                 /* ---- source (after the update, before the sponge: both families) */
-                if (a.src_on && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad &&
-                    j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad) {
+                if (src_cols && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad) {
                     FDW_UNROLL
                     for (int k = 0; k < 4; k++) {
                         int dj = j0 + k - a.src_j, di = gi - a.src_gi;
@@ -283,13 +269,6 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                     FDW_UNROLL
                     for (int k = 0; k < 4; k++)
                         if (j0 + k == a.inj_j) res[k] = fadd(res[k], s);
-                }
-                /* ---- columns outside the reference's truncated launch extent keep their value */
-                if (mupd != 0xFu) {
-                    const float4 raw = ld4(ppc);
-                    FDW_UNROLL
-                    for (int k = 0; k < 4; k++)
-                        if (!((mupd >> k) & 1u)) res[k] = getk(raw, k);
                 }
                 st4(ppc, make_float4(res[0], res[1], res[2], res[3]));
 
@@ -338,7 +317,7 @@ template <int ORDER>
 FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, int bdim)
 {
     constexpr int H = ORDER / 2, W = ORDER + 1;
-    const int q = bx * bdim + tid;
+    const int q = a.col4_0 + bx * bdim + tid;
     if (q >= a.ncol4) return;
     const int j0 = q * 4;
     const int rb = a.row0 + by * a.rows_per_cta;

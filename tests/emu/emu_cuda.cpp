@@ -36,6 +36,8 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = calloc(1, sizeof(double)); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t)
 {

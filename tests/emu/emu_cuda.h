@@ -22,7 +22,7 @@ enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
-enum { cudaStreamNonBlocking = 1 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
@@ -54,6 +54,8 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
 cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaEventCreate(cudaEvent_t *);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *, unsigned);
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned);
 cudaError_t cudaEventDestroy(cudaEvent_t);
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t);
 cudaError_t cudaEventSynchronize(cudaEvent_t);
