@@ -42,8 +42,8 @@ def main():
     x0, x1 = sp.slab
     sp.set_v2_local(v2[x0:x1])
     sp.set_wavelet(srce)
-    sp.set_source(x1 - 2 if rank == 0 else n // 2, nb)  # right next to a slab cut
-    na, nb_ = np.ascontiguousarray(a[x0:x1]), np.ascontiguousarray(b[x0:x1])
+    sp.set_source(D.slab_rows(n, world, 0)[1] - 2, nb)  # the same global point on every rank, next to a slab cut
+    na, nb_ = a[x0:x1].copy(), b[x0:x1].copy()  # copies: propagate_local works in place
     sp.propagate_local(na, nb_, 0, nt)
     torch.cuda.synchronize()
     parts = [None] * world
