@@ -22,3 +22,26 @@ def test_drivers_build_and_fail_loudly_without_gpu(tmp_path):
     p = subprocess.run([os.path.join(ROOT, "bin", "stencil_code"), "./input.dat", "o.bin"], cwd=tmp_path,
                        capture_output=True, text=True)
     assert p.returncode != 0 and "no CPU path" in p.stderr
+
+
+def test_shim_libraries_export_the_reference_symbols():
+    """libfdwave_cpufam.so / libfdwave_gpufam.so export exactly the (mangled) names the
+    reference's callers bind (include/fdwave_cpufam.h, include/fdwave_gpufam.h)."""
+    pkg = os.path.join(ROOT, "parallel_finite_difference_computation_b200")
+
+    def exported(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+        return {l.split()[-1] for l in out.splitlines() if " T " in l}
+
+    cpu = exported(os.path.join(pkg, "libfdwave_cpufam.so"))
+    want_cpu = {"_Z7fd_initiiifff", "_Z7fd_stepiPPfS0_S0_ii", "_Z10fd_destroyv", "_Z10calc_coefsi",
+                "_Z9extendveliiiiPf", "_Z10taper_initiif", "_Z11taper_applyPPfiiii", "_Z12taper_apply2PPfiiii",
+                "_Z13taper_destroyv", "_Z5ptsrciiiifPPf", "_Z14ricker_waveletiffPf", "_Z6rickerff"}
+    assert want_cpu <= cpu, want_cpu - cpu
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref_cpufam.so")
+    if os.path.exists(ref):  # the reference's own objects export the same names
+        assert want_cpu <= exported(ref)
+    gpu = exported(os.path.join(pkg, "libfdwave_gpufam.so"))
+    want_gpu = {"fd_init", "fd_init_cuda", "_Z13write_buffersPPfS0_S0_S_S_S0_S0_ii",
+                "_Z10fd_forwardiPPfS0_S0_iiiiiPiS_i", "_Z7fd_backiPPfS0_S0_S0_S0_iiiiiiPS0_S0_S0_"}
+    assert want_gpu <= gpu, want_gpu - gpu

@@ -168,3 +168,24 @@ def test_reference_forward_is_reproducible_and_equals_oracle():
         w.propagate(newest, older, 0, nt)
     PC.assert_bit_equal(newest, rPP, "libfdwave vs reference CUDA fd_forward PP")
     PC.assert_bit_equal(older, rP, "libfdwave vs reference CUDA fd_forward P")
+
+
+def test_reference_mains_relinked_against_our_shim(tmp_path, golden_dir):
+    """The truest drop-in test: the reference's UNMODIFIED mod_main.cpp and
+    rtm_main.cpp, linked against libfdwave_cpufam.so instead of the reference's fd.c /
+    taper.c / ptsrc.c (oracle/Makefile target `relinked`), must reproduce the shipped
+    3lay_mod golden files bit for bit with fd_step running on the GPU."""
+    if not R.path("mod_main_relinked"):
+        pytest.skip("oracle/_ref/mod_main_relinked not built")
+    d = os.path.join(golden_dir, "3lay_mod")
+    shutil.copy(os.path.join(d, "3layer_151x151.bin"), tmp_path / "3layer_151x151.bin")
+    (tmp_path / "input.dat").write_text(
+        "tmpdir=./\nvpfile=3layer_151x151.bin\ndatfile=dobs.bin\nnz=151\nnx=151\nnt=1001\ndz=10\ndx=10\n"
+        "dt=0.001\nfpeak=30.\nns=1\nsz=0\nfsx=0\nds=10\ngz=0\nnxb=40\nnzb=40\nfac=0.010\norder=8\n")
+    run([R.path("mod_main_relinked"), "par=input.dat"], tmp_path)
+    PC.assert_bit_equal(np.fromfile(tmp_path / "dobs.bin", np.float32),
+                        np.fromfile(os.path.join(d, "dobs.bin"), np.float32), "relinked mod_main dobs.bin")
+    run([R.path("rtm_main_relinked"), "par=input.dat"], tmp_path)
+    for f in ("dir.img", "dir.image"):
+        PC.assert_bit_equal(np.fromfile(tmp_path / f, np.float32), np.fromfile(os.path.join(d, f), np.float32),
+                            "relinked rtm_main " + f)
