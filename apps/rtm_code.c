@@ -56,7 +56,9 @@ int main(int argc, char **argv)
     prm.device = env_int("FDW_DEVICE", 0);
     prm.nt = nt;
     fdw_ctx *ctx = NULL;
+    const double t_io = now_s() - t_start;
     FDW(fdw_create(&prm, &ctx));
+    const double t_ctx = now_s() - t_start - t_io;
     FDW(fdw_set_wavelet(ctx, srce, nt));
 
     char path[1024];
@@ -94,8 +96,9 @@ int main(int argc, char **argv)
     }
     if (fnum) fclose(fnum);
     printf("> Exec time = %.2f (s)\n", (double)(long)(now_s() - t_start)); /* whole seconds, like fd-code.cu:536 */
-    fprintf(stderr, "[fdwave] %d shot(s), %d steps each: %.3f s in forward+backward (%.2f Gpts/s, 3 updates/pt/step)\n",
-            ns, nt, t_dev, 3.0 * ns * nt * (double)ne / t_dev / 1e9);
+    fprintf(stderr, "[fdwave] %d shot(s), %d steps each: %.3f s in forward+backward (%.2f Gpts/s, 3 updates/pt/step); "
+                    "input %.3f s, context %.3f s, total %.3f s\n",
+            ns, nt, t_dev, 3.0 * ns * nt * (double)ne / t_dev / 1e9, t_io, t_ctx, now_s() - t_start);
     snprintf(path, sizeof path, "%s/dir.image", in.tmpdir);
     write_floats(path, img, ni, "w");
     snprintf(path, sizeof path, "%s/dir.image_lap", in.tmpdir);

@@ -92,6 +92,7 @@ struct fdw_ctx {
     int nsm = 0;
     bool saved_valid = false;
     int rows_per_cta_override = 0, threads_override = 0;
+    long long small_grid_limit = 1LL << 18, fork_limit = 1LL << 20; /* in float4 columns x rows */
     /* split-phase step (slab decomposition) */
     bool step_open = false;
     StepArgs step_args;
@@ -167,6 +168,19 @@ static long long pitch_for(int nze) { return ((long long)nze + 4 + 31) / 32 * 32
  * tiling z; x is cut into chunks of rows_per_cta rows.  Measured on B200
  * (tools/kbench.cu): short chunks (16-32 rows) win -- the 8 halo rows a chunk
  * re-reads hit L2, while many small CTAs remove the wave-quantisation tail. */
+static int cached_occupancy(const void *kern, int nthreads)
+{
+    /* the occupancy query costs microseconds per call: remember it per (kernel, block size) */
+    static thread_local struct { const void *k; int nt, occ; } cache[64];
+    static thread_local int ncache = 0;
+    for (int i = 0; i < ncache; i++)
+        if (cache[i].k == kern && cache[i].nt == nthreads) return cache[i].occ;
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (ncache < 64) { cache[ncache].k = kern; cache[ncache].nt = nthreads; cache[ncache].occ = occ; ncache++; }
+    return occ;
+}
+
 static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int thr_override, int rpc_override,
                             dim3 *grid, dim3 *block, int *rows_per_cta)
 {
@@ -178,11 +192,9 @@ static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int 
     if (rpc_override > 0) {
         rpc = rpc_override;
     } else {
-        int occ = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, 0) != cudaSuccess || occ < 1) occ = 1;
-        const long long cap = (long long)nsm * occ;
+        const long long cap = (long long)nsm * cached_occupancy(kern, nthreads);
         /* small problems: shorten the chunks until the grid fills the machine twice over */
-        while (rpc > 8 && (long long)gx * ((rows + rpc - 1) / rpc) < 2 * cap) rpc /= 2;
+        while (rpc > 2 && (long long)gx * ((rows + rpc - 1) / rpc) < 2 * cap) rpc /= 2;
     }
     int gy = (rows + rpc - 1) / rpc;
     *grid = dim3(gx, gy < 1 ? 1 : gy, 1);
@@ -256,6 +268,12 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
         Rect all = {0, nc, row0, row1, 0};
         return launch_rect(c, base, recipe, epi, all, st);
     }
+    if ((long long)nc * (row1 - row0) < c->small_grid_limit) {
+        /* launch-bound regime (shipped models are ~0.1 Mpoint): one launch of the sponge kernel over
+         * everything -- its factors are exactly 1.0 outside the sponge, so the result is unchanged */
+        Rect all = {0, nc, row0, row1, 1};
+        return launch_rect(c, base, recipe, epi, all, st);
+    }
     /* columns whose own samples or z neighbours (+-4) sit in a z sponge, in whole warps */
     int cs = 0, cb = nc;
     if (c->tap_jlo > INT_MIN) cs = (((c->tap_jlo + 4 + 3) / 4) + 31) / 32 * 32;
@@ -268,18 +286,18 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
     if (c->tap_ihi < INT_MAX) { int v = c->tap_ihi - H - c->gx0; rh = v < rl ? rl : (v > row1 ? row1 : v); }
     Rect sponge[4] = {{0, cs, row0, row1, 1}, {cb, nc, row0, row1, 1}, {cs, cb, row0, rl, 1}, {cs, cb, rh, row1, 1}};
     Rect bulk = {cs, cb, rl, rh, 0};
-    const bool fork = bulk.c1 > bulk.c0 && bulk.r1 > bulk.r0;
+    /* fork only when the bulk launch is long enough to be worth two event operations */
+    const bool fork = bulk.c1 > bulk.c0 && bulk.r1 > bulk.r0 &&
+                      (long long)(bulk.c1 - bulk.c0) * (bulk.r1 - bulk.r0) >= c->fork_limit;
     cudaStream_t ss = fork ? c->side : st;
     if (fork) {
         CU(cudaEventRecord(c->ev_fork, st));
         CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
     }
     for (int k = 0; k < 4; k++) CHECK(launch_rect(c, base, recipe, epi, sponge[k], ss));
-    if (fork) {
-        CU(cudaEventRecord(c->ev_join, ss));
-        CHECK(launch_rect(c, base, recipe, epi, bulk, st));
-        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
-    }
+    if (fork) CU(cudaEventRecord(c->ev_join, ss));
+    CHECK(launch_rect(c, base, recipe, epi, bulk, st));
+    if (fork) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     return FDW_OK;
 }
 
@@ -465,6 +483,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     c->nsm = dp.multiProcessorCount;
     if (const char *e = getenv("FDW_ROWS_PER_CTA")) c->rows_per_cta_override = atoi(e);
     if (const char *e = getenv("FDW_THREADS")) c->threads_override = atoi(e);
+    if (const char *e = getenv("FDW_SMALL_GRID_LIMIT")) c->small_grid_limit = atoll(e);
+    if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
 
     /* coefficients and scalars: fd-code.cu:203-217 / fd.c:12-16 */
     float coefs[9];

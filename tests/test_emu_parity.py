@@ -14,6 +14,16 @@ def emu():
     return load_emu()
 
 
+@pytest.fixture(params=["one-launch", "rectangles", "rectangles+fork"])
+def launch_mode(request, monkeypatch):
+    """the library picks one sponge-kernel launch for tiny grids and plain/sponge rectangles
+    (optionally forked to a side stream) for large ones; force each path on the small test grids"""
+    if request.param != "one-launch":
+        monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+        monkeypatch.setenv("FDW_FORK_LIMIT", "0" if request.param.endswith("fork") else str(1 << 40))
+    return request.param
+
+
 @pytest.mark.parametrize("order", [2, 4, 6, 8])
 @pytest.mark.parametrize("shape", [(61, 47), (40, 64), (9, 9), (300, 130)])
 def test_stencil(emu, order, shape):
@@ -31,7 +41,7 @@ def test_stencil_golden(emu, golden_dir):
     (FAMILY_CPU, RECIPE_C, TAPER_TOP, SRC_POINT),
     (FAMILY_CPU, RECIPE_C, TAPER_FOUR, SRC_GAUSS7),
 ])
-def test_advance_bit_exact(emu, order, family, recipe, taper, src):
+def test_advance_bit_exact(emu, launch_mode, order, family, recipe, taper, src):
     PC.case_advance(emu, family, recipe, taper, order=order, src_kind=src)
 
 
@@ -42,14 +52,14 @@ def test_advance_nonzero_initial_fields(emu, family, recipe, taper):
 
 
 @pytest.mark.parametrize("dims", [(37, 29, 9, 8), (50, 43, 16, 16), (41, 35, 11, 13)])
-def test_advance_compat_extents(emu, dims):
+def test_advance_compat_extents(emu, launch_mode, dims):
     nx, nz, nxb, nzb = dims
     PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=nx, nz=nz, nxb=nxb, nzb=nzb, compat=True)
     PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=nx, nz=nz, nxb=nxb, nzb=nzb, compat=True,
                     random_init=True, nt=5)
 
 
-def test_advance_wide_grid_many_chunks(emu):
+def test_advance_wide_grid_many_chunks(emu, launch_mode):
     PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=90, nz=1100, nxb=10, nzb=12, nt=6)
 
 
@@ -59,15 +69,15 @@ def test_fast_recipe_within_tolerance(emu):
 
 @pytest.mark.parametrize("compat", [True, False])
 @pytest.mark.parametrize("roundtrip", [True, False])
-def test_gpu_family_rtm_shot(emu, compat, roundtrip):
+def test_gpu_family_rtm_shot(emu, launch_mode, compat, roundtrip):
     PC.case_gpu_rtm(emu, compat=compat, host_roundtrip=roundtrip)
 
 
-def test_mod_main_shot(emu):
+def test_mod_main_shot(emu, launch_mode):
     PC.case_mod_shot(emu)
     PC.case_mod_shot(emu, order=4, nx=30, nz=41, nxb=5, nzb=9)
 
 
 @pytest.mark.parametrize("is_", [0, 1])
-def test_rtm_main_shot(emu, is_):
+def test_rtm_main_shot(emu, launch_mode, is_):
     PC.case_rtm_shot_cpu(emu, is_=is_)

@@ -33,6 +33,14 @@ def test_stencil_golden_output_teste(lib, golden_dir):
     PC.case_stencil_golden(lib, golden_dir)
 
 
+@pytest.fixture(params=["one-launch", "rectangles+fork"])
+def launch_mode(request, monkeypatch):
+    if request.param != "one-launch":
+        monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+        monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("order", [2, 4, 6, 8])
 @pytest.mark.parametrize("family,recipe,taper,src", [
     (FAMILY_GPU, RECIPE_G, TAPER_TOP, SRC_POINT),
@@ -40,7 +48,7 @@ def test_stencil_golden_output_teste(lib, golden_dir):
     (FAMILY_CPU, RECIPE_C, TAPER_TOP, SRC_POINT),
     (FAMILY_CPU, RECIPE_C, TAPER_FOUR, SRC_GAUSS7),
 ])
-def test_advance_bit_exact(lib, order, family, recipe, taper, src):
+def test_advance_bit_exact(lib, launch_mode, order, family, recipe, taper, src):
     PC.case_advance(lib, family, recipe, taper, order=order, src_kind=src)
 
 
@@ -72,18 +80,18 @@ def test_fast_recipe_within_tolerance(lib):
 
 @pytest.mark.parametrize("compat", [True, False])
 @pytest.mark.parametrize("roundtrip", [True, False])
-def test_gpu_family_rtm_shot(lib, compat, roundtrip):
+def test_gpu_family_rtm_shot(lib, launch_mode, compat, roundtrip):
     PC.case_gpu_rtm(lib, compat=compat, host_roundtrip=roundtrip)
     PC.case_gpu_rtm(lib, nx=150, nz=130, nxb=24, nzb=24, nt=300, compat=compat, host_roundtrip=roundtrip)
 
 
-def test_mod_main_shot(lib):
+def test_mod_main_shot(lib, launch_mode):
     PC.case_mod_shot(lib)
     PC.case_mod_shot(lib, order=4, nx=30, nz=41, nxb=5, nzb=9)
 
 
 @pytest.mark.parametrize("is_", [0, 1])
-def test_rtm_main_shot(lib, is_):
+def test_rtm_main_shot(lib, launch_mode, is_):
     PC.case_rtm_shot_cpu(lib, is_=is_)
 
 
