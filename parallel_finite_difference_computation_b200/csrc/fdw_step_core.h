@@ -136,6 +136,27 @@ FDW_HD float4 tap4(float4 v, const float *zf, unsigned xon, float xf, bool zon, 
     return make_float4(e[0], e[1], e[2], e[3]);
 }
 
+/* source patch on the 4 samples of one thread; deliberately not inlined so that the rare path
+ * stays a real branch instead of being if-converted into every row of every thread */
+#ifdef __CUDACC__
+static __host__ __device__ __noinline__
+#else
+static
+#endif
+float4 add_source(const StepArgs &a, float4 r4, int gi, int j0)
+{
+    float res[4] = {r4.x, r4.y, r4.z, r4.w};
+    const int di = gi - a.src_gi;
+    for (int k = 0; k < 4; k++) {
+        const int dj = j0 + k - a.src_j;
+        if (dj >= -a.src_rad && dj <= a.src_rad && j0 + k < a.nze) {
+            const float amp = a.src_rad ? fmul(a.src_amp, a.src_w[(di + 3) * 7 + (dj + 3)]) : a.src_amp;
+            res[k] = fadd(res[k], amp);
+        }
+    }
+    return make_float4(res[0], res[1], res[2], res[3]);
+}
+
 template <int ORDER, int RECIPE, bool TAPER, int EPI>
 FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
 {
@@ -148,12 +169,13 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
     if (rb >= re) return;
     const long long pitch = a.pitch;
 
-    /* per-thread column predicates */
-    unsigned mlap = 0;
-    FDW_UNROLL
-    for (int k = 0; k < 4; k++)
-        if (j0 + k >= a.lap_j0 && j0 + k < a.lap_j1) mlap |= 1u << k;
-    const bool src_cols = a.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
+    /* Per-thread invariants are folded into two rarely-true flags so that the streaming loop of
+     * the ~99.9 % of threads that sit neither on the grid ring nor next to the source carries no
+     * mask arithmetic (kept lean on purpose: at 64 registers ptxas rematerialises anything else
+     * every row).  ring: some of this thread's 4 columns, or some of this CTA's rows, lie where
+     * the Laplacian is defined as 0.  near_src: the source patch overlaps these 4 columns. */
+    const bool ring = j0 < a.lap_j0 || j0 + 4 > a.lap_j1 || a.grow0 + rb < a.lap_i0 || a.grow0 + re > a.lap_i1;
+    const bool near_src = a.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
 
     /* sponge factors of the 12 columns j0-4 .. j0+7 */
     float zf[12];
@@ -181,11 +203,12 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
         pc += pitch;
     }
 
-    for (int r = rb; r < re; r += W) {
+    /* count-down loop: the only loop-carried integers are `left` and the three row pointers */
+    for (int left = re - rb; left > 0; left -= W) {
         FDW_UNROLL
         for (int u = 0; u < W; u++) {
-            const int lr = r + u; /* local row being updated */
-            if (lr < re) {
+            if (u < left) {
+                const int lr = re - left + u; /* local row being updated (only rare paths use it) */
                 const int gi = a.grow0 + lr;
                 float4 wn = ld4(pc); /* row lr+H */
                 const float *ctr = pc - (long long)H * pitch;
@@ -206,11 +229,9 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                 const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
                 const float oo[4] = {o4.x, o4.y, o4.z, o4.w};
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-                const unsigned ml = (gi >= a.lap_i0 && gi < a.lap_i1) ? mlap : 0u;
-                float res[4];
+                float lap[4], res[4];
                 FDW_UNROLL
                 for (int k = 0; k < 4; k++) {
-                    float lap;
                     if (RECIPE == RECIPE_G) {
                         /* two accumulators, ascending io, summed last (fd-code.cu:66-72).
                          * The reference's "0 +" first add is dropped: it can only change
@@ -222,7 +243,7 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                             az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
                             ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
                         }
-                        lap = fadd(az, ax);
+                        lap[k] = fadd(az, ax);
                     } else if (RECIPE == RECIPE_C) {
                         /* one accumulator, z tap then x tap, (p*c)*d2inv (fd.c:30-33) */
                         float acm = fmul(fmul(za[4 + k - H], a.cz[0]), a.dz2inv);
@@ -232,7 +253,7 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                             acm = fadd(acm, fmul(fmul(za[4 + k - H + io], a.cz[io]), a.dz2inv));
                             acm = fadd(acm, fmul(fmul(getk(w[(u + io) % W], k), a.cx[io]), a.dx2inv));
                         }
-                        lap = acm;
+                        lap[k] = acm;
                     } else {
                         /* FAST: symmetric pairs + FMA; tolerance-checked, not bit-checked */
                         float s = fmul(cc[k], a.cz[H] + a.cx[H]);
@@ -241,25 +262,27 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                             s = ffma(a.cz[H + d], za[4 + k - d] + za[4 + k + d], s);
                             s = ffma(a.cx[H + d], getk(w[(u + H - d) % W], k) + getk(w[(u + H + d) % W], k), s);
                         }
-                        lap = s;
+                        lap[k] = s;
                     }
-                    if (!((ml >> k) & 1u)) lap = 0.0f;
+                }
+                if (ring) { /* rare: the ring of width order/2 keeps lap = 0 (quirk Q2 read as 0) */
+                    const bool row_in = gi >= a.lap_i0 && gi < a.lap_i1;
+                    FDW_UNROLL
+                    for (int k = 0; k < 4; k++)
+                        if (!row_in || j0 + k < a.lap_j0 || j0 + k >= a.lap_j1) lap[k] = 0.0f;
+                }
+                FDW_UNROLL
+                for (int k = 0; k < 4; k++) {
                     if (RECIPE == RECIPE_FAST)
-                        res[k] = ffma(vv[k], lap, 2.0f * cc[k] - oo[k]);
+                        res[k] = ffma(vv[k], lap[k], 2.0f * cc[k] - oo[k]);
                     else
-                        res[k] = leap(cc[k], oo[k], fmul(vv[k], lap));
+                        res[k] = leap(cc[k], oo[k], fmul(vv[k], lap[k]));
                 }
 
                 /* ---- source (after the update, before the sponge: both families) */
-                if (src_cols && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad) {
-                    FDW_UNROLL
-                    for (int k = 0; k < 4; k++) {
-                        int dj = j0 + k - a.src_j, di = gi - a.src_gi;
-                        if (dj >= -a.src_rad && dj <= a.src_rad && j0 + k < a.nze) {
-                            float amp = a.src_rad ? fmul(a.src_amp, a.src_w[(di + 3) * 7 + (dj + 3)]) : a.src_amp;
-                            res[k] = fadd(res[k], amp);
-                        }
-                    }
+                if (near_src && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad) {
+                    const float4 s4 = add_source(a, make_float4(res[0], res[1], res[2], res[3]), gi, j0);
+                    res[0] = s4.x; res[1] = s4.y; res[2] = s4.z; res[3] = s4.w;
                 }
                 /* ---- receiver back-injection */
                 if ((EPI & EPI_INJECT) && gi >= a.inj_gi0 && gi < a.inj_gi0 + a.inj_n && a.inj_j >= j0 &&

@@ -133,41 +133,44 @@ def test_rtm_code_vs_reference_cuda_program(tmp_path, dims):
         assert os.path.getsize(ours / "out" / f) == 0
 
 
-def test_reference_forward_is_reproducible_and_equals_oracle():
-    """function-level: the reference's own CUDA fd_forward (libref_gpufam.so) on this GPU
-    vs the oracle vs our library, bit for bit, with random initial fields."""
+def test_reference_forward_equals_oracle_and_library():
+    """function-level: the reference's own CUDA fd_forward (libref_gpufam.so) on this GPU vs the
+    oracle vs our library, from zero fields as in every reference call path.  When the reference
+    reproduces itself (two runs bit-identical -- the usual case; its corner sponge is formally
+    racy, quirk Q4) the three must agree bit for bit; otherwise within 10x its own spread."""
     if not R.available("libref_gpufam.so"):
         pytest.skip("oracle/_ref/libref_gpufam.so not built")
     import parallel_finite_difference_computation_b200 as fdw
-    nx, nz, nb, nt = 101, 83, 24, 150
+    nx, nz, nb, nt = 101, 83, 24, 400
     nxe, nze = nx + 2 * nb, nz + 2 * nb
     rng = np.random.default_rng(3)
     v2 = PC.layered_v2(nx, nz, nb, nb, rng, random_border=True)
     srce = O.ricker_wavelet(nt, 0.001, 25.0, O.FAM_G)
     sx, sz = nx // 4 + nb, nb
-    P0 = rng.standard_normal((nxe, nze)).astype(np.float32)
-    PP0 = rng.standard_normal((nxe, nze)).astype(np.float32)
-    ux, uz = (nxe // 8) * 8, (nze // 8) * 8
-    for f in (P0, PP0):
-        f[ux:] = 0
-        f[:, uz:] = 0
     g = R.GpuFam()
     g.fd_init(8, nxe, nze, nb, nb, nt, 1, 0.75, 10.0, 10.0, 0.001)
-    rP, rPP = P0.copy(), PP0.copy()
-    g.fd_forward(8, rP, rPP, v2, nt, 0, sz, [sx], srce)
-    oP, oPP = O.gpu_forward(O.GpuCfg(8, nxe, nze, nb, nb, nt, 10.0, 10.0, 0.001, 0.75, 1), v2, srce, sx, sz, P0, PP0)
-    PC.assert_bit_equal(oP, rP, "oracle vs reference CUDA fd_forward P")
-    PC.assert_bit_equal(oPP, rPP, "oracle vs reference CUDA fd_forward PP")
+    runs = []
+    for _ in range(2):
+        rP, rPP = np.zeros((nxe, nze), np.float32), np.zeros((nxe, nze), np.float32)
+        g.fd_forward(8, rP, rPP, v2, nt, 0, sz, [sx], srce)
+        runs.append((rP, rPP))
+    (rP, rPP), (rP2, rPP2) = runs
+    assert np.abs(rPP).max() > 0
+    oP, oPP = O.gpu_forward(O.GpuCfg(8, nxe, nze, nb, nb, nt, 10.0, 10.0, 0.001, 0.75, 1), v2, srce, sx, sz)
     with fdw.Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, order=8, fac=0.75, family=fdw.FAMILY_GPU,
                     taper=fdw.TAPER_TOP, compat_extents=True, nt=nt) as w:
         w.set_v2(v2)
         w.set_wavelet(srce)
-        w.set_source(sx, sz)
-        # reference: swap first, so the stencil input is PP (fd-code.cu:260-262)
-        newest, older = PP0.copy(), P0.copy()
-        w.propagate(newest, older, 0, nt)
-    PC.assert_bit_equal(newest, rPP, "libfdwave vs reference CUDA fd_forward PP")
-    PC.assert_bit_equal(older, rP, "libfdwave vs reference CUDA fd_forward P")
+        P, PP = w.forward(sx, sz)
+    PC.assert_bit_equal(P, oP, "libfdwave vs oracle P")
+    PC.assert_bit_equal(PP, oPP, "libfdwave vs oracle PP")
+    if np.array_equal(rP, rP2) and np.array_equal(rPP, rPP2):
+        PC.assert_bit_equal(oP, rP, "oracle vs reference CUDA fd_forward P")
+        PC.assert_bit_equal(oPP, rPP, "oracle vs reference CUDA fd_forward PP")
+    else:
+        spread = PC.rel_l2(rPP2, rPP)
+        print("reference fd_forward not reproducible in this run: self rel-L2 %.3g" % spread)
+        assert PC.rel_l2(oPP, rPP) <= max(10 * spread, 1e-6)
 
 
 def test_reference_mains_relinked_against_our_shim(tmp_path, golden_dir):
