@@ -179,6 +179,19 @@ typedef struct fdw_halo {
     void *recv_lo, *recv_hi; /* ghost rows below row 0 / above row nloc-1 */
     long long count;         /* floats per block */
 } fdw_halo;
+/* shot phases for the split-phase API: fdw_shot_begin prepares a phase (zero fields, record /
+ * history / image / trace buffers), the caller then drives params.nt levels with
+ * fdw_step_begin/rows/end, and fdw_shot_end downloads THIS SLAB's part of the result:
+ *   FDW_PHASE_MODEL    mod_main shot        -> traces of the owned interior x rows, [nli][nt]
+ *   FDW_PHASE_RTM_FWD  rtm_main forward     -> nothing (history stays in HBM; no fdw_shot_end)
+ *   FDW_PHASE_RTM_BWD  rtm_main backward    -> image rows of the owned interior x rows, [nli][nz]
+ * (owned interior rows: fdw_devinfo.li0 / nli).  dobs_all is the whole [ns][nx][nt] block. */
+#define FDW_PHASE_PLAIN 0
+#define FDW_PHASE_MODEL 1
+#define FDW_PHASE_RTM_FWD 2
+#define FDW_PHASE_RTM_BWD 3
+int fdw_shot_begin(fdw_ctx *ctx, int phase, int sx, int sz, int gz, const float *dobs_all, int ns, int is);
+int fdw_shot_end(fdw_ctx *ctx, float *out);
 int fdw_step_begin(fdw_ctx *ctx, int it);
 int fdw_step_rows(fdw_ctx *ctx, int row0, int row1, void *cuda_stream);
 int fdw_step_end(fdw_ctx *ctx);
@@ -195,6 +208,7 @@ typedef struct fdw_devinfo {
     void *vdt;
     long long pitch; /* floats */
     int nloc, gx0, nxe, nze, guard;
+    int li0, nli; /* interior x rows owned by this context: global rows [li0, li0+nli) */
 } fdw_devinfo;
 int fdw_devinfo_get(fdw_ctx *ctx, fdw_devinfo *out);
 /* device time of the work enqueued between mark_begin and mark_end, in ms

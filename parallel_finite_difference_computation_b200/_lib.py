@@ -17,6 +17,7 @@ FAMILY_GPU, FAMILY_CPU = 0, 1
 RECIPE_G, RECIPE_C, RECIPE_FAST = 0, 1, 2
 TAPER_NONE, TAPER_TOP, TAPER_FOUR = 0, 1, 2
 SRC_POINT, SRC_GAUSS7 = 0, 1
+PHASE_PLAIN, PHASE_MODEL, PHASE_RTM_FWD, PHASE_RTM_BWD = 0, 1, 2, 3
 
 f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
@@ -52,7 +53,8 @@ class Halo(C.Structure):
 
 class DevInfo(C.Structure):
     _fields_ = [("newest", C.c_void_p), ("older", C.c_void_p), ("vdt", C.c_void_p), ("pitch", C.c_longlong),
-                ("nloc", C.c_int), ("gx0", C.c_int), ("nxe", C.c_int), ("nze", C.c_int), ("guard", C.c_int)]
+                ("nloc", C.c_int), ("gx0", C.c_int), ("nxe", C.c_int), ("nze", C.c_int), ("guard", C.c_int),
+                ("li0", C.c_int), ("nli", C.c_int)]
 
 
 # every symbol include/fdwave.h declares: (restype, argtypes)
@@ -86,6 +88,8 @@ SIGNATURES = {
     "fdw_model_shot": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p]),
     "fdw_rtm_shot_cpu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p]),
     "fdw_stencil": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, f32p, C.c_int]),
+    "fdw_shot_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _optf32, C.c_int, C.c_int]),
+    "fdw_shot_end": (C.c_int, [C.c_void_p, f32p]),
     "fdw_step_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "fdw_step_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "fdw_step_end": (C.c_int, [C.c_void_p]),

@@ -93,6 +93,9 @@ struct fdw_ctx {
     bool saved_valid = false;
     int rows_per_cta_override = 0, threads_override = 0;
     long long small_grid_limit = 1LL << 18, fork_limit = 1LL << 20; /* in float4 columns x rows */
+    int li0 = 0, nli = 0; /* interior x rows owned by this slab: global rows [li0, li0+nli) */
+    /* split-phase shot state (slab decomposition) */
+    int phase = 0, shot_gz = 0, shot_is = 0, shot_ns = 1;
     /* split-phase step (slab decomposition) */
     bool step_open = false;
     StepArgs step_args;
@@ -473,6 +476,11 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
         c->gx0 = prm->slab_x0;
         c->nloc = prm->slab_x1 - prm->slab_x0;
     }
+    c->li0 = prm->nxb > c->gx0 ? prm->nxb : c->gx0;
+    {
+        int hi = prm->nxb + prm->nx < c->gx0 + c->nloc ? prm->nxb + prm->nx : c->gx0 + c->nloc;
+        c->nli = hi > c->li0 ? hi - c->li0 : 0;
+    }
     c->pitch = pitch_for(c->nze);
     c->rows_alloc = (size_t)c->nloc + 2 * GUARD + 2;
     c->field_elems = c->rows_alloc * (size_t)c->pitch;
@@ -550,7 +558,7 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     TRY(cudaMemcpyAsync(c->tx_base, tx.data(), tx.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     c->tz = c->tz_base + 4;
     c->tx = c->tx_base + GUARD;
-    const size_t img_elems = (size_t)prm->nx * c->pitch;
+    const size_t img_elems = (size_t)(c->nli > 0 ? c->nli : 1) * c->pitch; /* image/history rows = owned interior rows */
     TRY(cudaMalloc(&c->img, img_elems * sizeof(float)));
     TRY(cudaMemsetAsync(c->img, 0, img_elems * sizeof(float), c->stream));
     if (prm->history) {
@@ -714,8 +722,9 @@ static int ensure_buffer(float **buf, size_t *cap, size_t need)
 static int image_download(fdw_ctx *c, float *imloc)
 {
     const fdw_params &p = c->prm;
-    CU(cudaMemcpy2DAsync(imloc, (size_t)p.nz * sizeof(float), c->img + p.nzb, c->pitch * sizeof(float),
-                         (size_t)p.nz * sizeof(float), p.nx, cudaMemcpyDeviceToHost, c->stream));
+    if (c->nli > 0)
+        CU(cudaMemcpy2DAsync(imloc, (size_t)p.nz * sizeof(float), c->img + p.nzb, c->pitch * sizeof(float),
+                             (size_t)p.nz * sizeof(float), c->nli, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return FDW_OK;
 }
@@ -736,6 +745,7 @@ extern "C" int fdw_backward(fdw_ctx *c, const float *P, const float *PP, const f
     /* time-reversed roles: S_0 = PP, S_1 = P (fd-code.cu:304-314) */
     int s_pp = c->newest[0], s_p = c->older[0];
     CHECK(fdw_fields_zero(c, 1));
+    if (c->nli != p.nx) { fdw_set_error("fdw_backward: not available on a slab context"); return FDW_ERR_UNSUPPORTED; }
     CU(cudaMemsetAsync(c->img, 0, (size_t)p.nx * c->pitch * sizeof(float), c->stream));
     const size_t ntr = (size_t)p.nx * nt;
     CHECK(ensure_buffer(&c->dobs_d, &c->dobs_cap, ntr));
@@ -768,60 +778,125 @@ extern "C" int fdw_backward(fdw_ctx *c, const float *P, const float *PP, const f
     return image_download(c, imloc);
 }
 
+/* ---- the three CPU-family shot phases, shared by the one-call pipelines below and by the
+ * split-phase (slab) API: which epilogue runs and what it is given at time level `it` */
+enum { PHASE_PLAIN = FDW_PHASE_PLAIN, PHASE_MODEL = FDW_PHASE_MODEL, PHASE_RTM_FWD = FDW_PHASE_RTM_FWD,
+       PHASE_RTM_BWD = FDW_PHASE_RTM_BWD };
+
+static int phase_epi(int phase)
+{
+    switch (phase) {
+    case PHASE_MODEL: return fdw::EPI_RECORD;
+    case PHASE_RTM_FWD: return fdw::EPI_HSTORE;
+    case PHASE_RTM_BWD: return fdw::EPI_INJECT | fdw::EPI_IMG_HIST;
+    default: return 0;
+    }
+}
+
+static void phase_fill(const fdw_ctx *c, int phase, int it, StepArgs &a)
+{
+    const fdw_params &p = c->prm;
+    const int nt = p.nt;
+    const size_t slice = (size_t)(c->nli > 0 ? c->nli : 1) * c->pitch;
+    if (phase == PHASE_MODEL) { /* mod_main.cpp:159-161 */
+        a.rec = c->rec_d; a.rec_gi0 = c->li0; a.rec_n = c->nli; a.rec_j = c->shot_gz; a.rec_nt = nt; a.rec_it = it;
+    } else if (phase == PHASE_RTM_FWD) { /* rtm_main.cpp:177-181 */
+        a.hist_w = c->hist + (size_t)it * slice; a.hist_gi0 = c->li0; a.hist_n = c->nli;
+    } else if (phase == PHASE_RTM_BWD) { /* rtm_main.cpp:201-203, 223-229 */
+        a.dobs = c->dobs_d;
+        a.dobs_base = (long long)c->shot_is * p.nx * nt;
+        a.dobs_len = (long long)c->shot_ns * p.nx * nt;
+        a.inj_gi0 = p.nzb; /* quirk Q5: rtm_main.cpp:202 offsets x by nzb */
+        a.inj_n = p.nx; a.inj_j = c->shot_gz; a.inj_nt = nt; a.inj_tidx = nt - it; /* Q5: nt-it */
+        a.hist_r = c->hist + (size_t)(nt - 1 - it) * slice; a.hist_gi0 = c->li0; a.hist_n = c->nli;
+        a.img = c->img; a.img_gi0 = c->li0; a.img_n = c->nli;
+    }
+}
+
+/* prepare buffers for one phase of a shot (fields zeroed; record / image / traces set up) */
+static int phase_begin(fdw_ctx *c, int phase, int sx, int sz, int gz, const float *dobs_all, int ns, int is)
+{
+    const fdw_params &p = c->prm;
+    const int nt = p.nt;
+    if (nt < 1 || c->wavelet.size() < (size_t)nt) { fdw_set_error("shot: params.nt / wavelet not set"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    CHECK(fdw_fields_zero(c, 0));
+    c->phase = phase; c->shot_gz = gz; c->shot_is = is; c->shot_ns = ns;
+    const size_t slice = (size_t)(c->nli > 0 ? c->nli : 1) * c->pitch;
+    if (phase == PHASE_MODEL) {
+        CHECK(fdw_set_source(c, sx, sz, FDW_SRC_GAUSS7));
+        const size_t ntr = (size_t)(c->nli > 0 ? c->nli : 1) * nt;
+        CHECK(ensure_buffer(&c->rec_d, &c->rec_cap, ntr));
+        CU(cudaMemsetAsync(c->rec_d, 0, ntr * sizeof(float), c->stream));
+    } else if (phase == PHASE_RTM_FWD) {
+        if (!c->hist) { fdw_set_error("shot: context created without params.history"); return FDW_ERR_STATE; }
+        CHECK(fdw_set_source(c, sx, sz, FDW_SRC_POINT));
+    } else if (phase == PHASE_RTM_BWD) {
+        if (!c->hist || !dobs_all) { fdw_set_error("shot: history / traces missing"); return FDW_ERR_STATE; }
+        CU(cudaMemsetAsync(c->img, 0, slice * sizeof(float), c->stream));
+        const size_t ntot = (size_t)ns * p.nx * nt;
+        CHECK(ensure_buffer(&c->dobs_d, &c->dobs_cap, ntot));
+        CU(cudaMemcpyAsync(c->dobs_d, dobs_all, ntot * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    return FDW_OK;
+}
+
+static int phase_run(fdw_ctx *c, int phase)
+{
+    const int nt = c->prm.nt;
+    const bool source = phase != PHASE_RTM_BWD;
+    for (int it = 0; it < nt; it++)
+        CHECK(step_pair(c, 0, c->prm.recipe, phase_epi(phase), true, source, it,
+                        [&](StepArgs &a) { phase_fill(c, phase, it, a); }));
+    return FDW_OK;
+}
+
 extern "C" int fdw_model_shot(fdw_ctx *c, int sx, int sz, int gz, float *data)
 {
     if (!c || !data) return FDW_ERR_ARG;
-    const fdw_params &p = c->prm;
-    const int nt = p.nt;
-    if (nt < 1 || c->wavelet.size() < (size_t)nt) { fdw_set_error("fdw_model_shot: nt / wavelet not set"); return FDW_ERR_STATE; }
-    CHECK(bind(c));
-    CHECK(fdw_fields_zero(c, 0));
-    CHECK(fdw_set_source(c, sx, sz, FDW_SRC_GAUSS7));
-    const size_t ntr = (size_t)p.nx * nt;
-    CHECK(ensure_buffer(&c->rec_d, &c->rec_cap, ntr));
-    CU(cudaMemsetAsync(c->rec_d, 0, ntr * sizeof(float), c->stream));
-    for (int it = 0; it < nt; it++)
-        CHECK(step_pair(c, 0, p.recipe, fdw::EPI_RECORD, true, true, it, [&](StepArgs &a) {
-            a.rec = c->rec_d; a.rec_gi0 = p.nxb; a.rec_n = p.nx; a.rec_j = gz; a.rec_nt = nt; a.rec_it = it;
-        }));
-    CU(cudaMemcpyAsync(data, c->rec_d, ntr * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return FDW_OK;
+    CHECK(phase_begin(c, PHASE_MODEL, sx, sz, gz, nullptr, 1, 0));
+    CHECK(phase_run(c, PHASE_MODEL));
+    return fdw_shot_end(c, data);
 }
 
 extern "C" int fdw_rtm_shot_cpu(fdw_ctx *c, int sx, int sz, int gz, const float *dobs_all, int ns, int is,
                                 float *imloc)
 {
     if (!c || !dobs_all || !imloc || ns < 1 || is < 0 || is >= ns) return FDW_ERR_ARG;
-    const fdw_params &p = c->prm;
-    const int nt = p.nt;
-    if (!c->hist) { fdw_set_error("fdw_rtm_shot_cpu: context created without params.history"); return FDW_ERR_STATE; }
-    if (nt < 1 || c->wavelet.size() < (size_t)nt) { fdw_set_error("fdw_rtm_shot_cpu: nt / wavelet not set"); return FDW_ERR_STATE; }
-    CHECK(bind(c));
-    const size_t slice = (size_t)p.nx * c->pitch;
     /* forward with history (rtm_main.cpp:166-188) */
-    CHECK(fdw_fields_zero(c, 0));
-    CHECK(fdw_set_source(c, sx, sz, FDW_SRC_POINT));
-    for (int it = 0; it < nt; it++)
-        CHECK(step_pair(c, 0, p.recipe, fdw::EPI_HSTORE, true, true, it, [&](StepArgs &a) {
-            a.hist_w = c->hist + (size_t)it * slice; a.hist_gi0 = p.nxb; a.hist_n = p.nx;
-        }));
-    /* backward + imaging on the fly (rtm_main.cpp:196-229): imloc += swf[nt-1-it]*rwf[it],
-     * it ascending -- the same float summation order as the reference's third loop */
-    CHECK(fdw_fields_zero(c, 0));
-    CU(cudaMemsetAsync(c->img, 0, slice * sizeof(float), c->stream));
-    const size_t ntot = (size_t)ns * p.nx * nt;
-    CHECK(ensure_buffer(&c->dobs_d, &c->dobs_cap, ntot));
-    CU(cudaMemcpyAsync(c->dobs_d, dobs_all, ntot * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    for (int it = 0; it < nt; it++)
-        CHECK(step_pair(c, 0, p.recipe, fdw::EPI_INJECT | fdw::EPI_IMG_HIST, true, false, it, [&](StepArgs &a) {
-            a.dobs = c->dobs_d; a.dobs_base = (long long)is * p.nx * nt; a.dobs_len = (long long)ntot;
-            a.inj_gi0 = p.nzb; /* quirk Q5: rtm_main.cpp:202 offsets x by nzb */
-            a.inj_n = p.nx; a.inj_j = gz; a.inj_nt = nt; a.inj_tidx = nt - it; /* Q5: nt-it */
-            a.hist_r = c->hist + (size_t)(nt - 1 - it) * slice; a.hist_gi0 = p.nxb; a.hist_n = p.nx;
-            a.img = c->img; a.img_gi0 = p.nxb; a.img_n = p.nx;
-        }));
-    return image_download(c, imloc);
+    CHECK(phase_begin(c, PHASE_RTM_FWD, sx, sz, gz, nullptr, ns, is));
+    CHECK(phase_run(c, PHASE_RTM_FWD));
+    /* backward + imaging on the fly (rtm_main.cpp:196-229): imloc += swf[nt-1-it]*rwf[it], it ascending --
+     * the same float summation order as the reference's third loop, so rwf is never stored */
+    CHECK(phase_begin(c, PHASE_RTM_BWD, sx, sz, gz, dobs_all, ns, is));
+    CHECK(phase_run(c, PHASE_RTM_BWD));
+    return fdw_shot_end(c, imloc);
+}
+
+/* split-phase versions (slab decomposition): the caller drives the levels with
+ * fdw_step_begin / fdw_step_rows / fdw_step_end and exchanges halos in between */
+extern "C" int fdw_shot_begin(fdw_ctx *c, int phase, int sx, int sz, int gz, const float *dobs_all, int ns, int is)
+{
+    if (!c || phase < PHASE_PLAIN || phase > PHASE_RTM_BWD) return FDW_ERR_ARG;
+    if (phase == PHASE_PLAIN) { c->phase = phase; return FDW_OK; }
+    return phase_begin(c, phase, sx, sz, gz, dobs_all, ns, is);
+}
+
+extern "C" int fdw_shot_end(fdw_ctx *c, float *out)
+{
+    if (!c || !out) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    const int phase = c->phase;
+    c->phase = PHASE_PLAIN;
+    if (phase == PHASE_MODEL) { /* this slab's traces, [nli][nt] */
+        const size_t ntr = (size_t)c->nli * c->prm.nt;
+        if (ntr) CU(cudaMemcpyAsync(out, c->rec_d, ntr * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return FDW_OK;
+    }
+    if (phase == PHASE_RTM_BWD) return image_download(c, out); /* this slab's image rows, [nli][nz] */
+    fdw_set_error("fdw_shot_end: phase %d has no host output", phase);
+    return FDW_ERR_STATE;
 }
 
 /* ------------------------------------------------------------------ stencil program */
@@ -883,7 +958,8 @@ extern "C" int fdw_step_begin(fdw_ctx *c, int it)
     if (tap && c->prm.family == FDW_FAMILY_GPU) { n.pend++; o.pend++; }
     base_args(c, 0, &c->step_args);
     c->step_args.taper_on = (n.pend || o.pend) ? 1 : 0;
-    if (!c->wavelet.empty()) set_source_args(c, &c->step_args, it);
+    if (!c->wavelet.empty() && c->phase != PHASE_RTM_BWD) set_source_args(c, &c->step_args, it);
+    phase_fill(c, c->phase, it, c->step_args);
     c->step_open = true;
     return FDW_OK;
 }
@@ -893,7 +969,8 @@ extern "C" int fdw_step_rows(fdw_ctx *c, int row0, int row1, void *stream)
     if (!c) return FDW_ERR_ARG;
     if (!c->step_open) { fdw_set_error("fdw_step_rows: no open step"); return FDW_ERR_STATE; }
     CHECK(bind(c));
-    return launch_level(c, c->step_args, c->prm.recipe, 0, row0, row1, stream ? (cudaStream_t)stream : c->stream);
+    return launch_level(c, c->step_args, c->prm.recipe, phase_epi(c->phase), row0, row1,
+                        stream ? (cudaStream_t)stream : c->stream);
 }
 
 extern "C" int fdw_step_end(fdw_ctx *c)
@@ -984,6 +1061,7 @@ extern "C" int fdw_devinfo_get(fdw_ctx *c, fdw_devinfo *o)
     o->vdt = c->vdt;
     o->pitch = c->pitch;
     o->nloc = c->nloc; o->gx0 = c->gx0; o->nxe = c->nxe; o->nze = c->nze; o->guard = GUARD;
+    o->li0 = c->li0; o->nli = c->nli;
     return FDW_OK;
 }
 

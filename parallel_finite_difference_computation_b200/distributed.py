@@ -32,8 +32,11 @@ def slab_rows(nxe, world, rank):
     return x0, x1
 
 
-def shot_partition(ns, world, rank):
-    """shots handled by `rank` (round-robin keeps the load even when ns % world != 0)"""
+def shot_partition(ns, world, rank, contiguous=False):
+    """shots handled by `rank`: round-robin (even load when ns % world != 0), or contiguous
+    blocks (needed by the bit-reproducible chained image stack, stack_images_chain)"""
+    if contiguous:
+        return list(range((ns * rank) // world, (ns * (rank + 1)) // world))
     return list(range(rank, ns, world))
 
 
@@ -143,13 +146,68 @@ class SlabPropagator:
             import torch
             torch.cuda.current_stream().synchronize()
 
+    # -- slab-decomposed shots of the CPU family (config 5: mod_main + rtm_main, domain-divided)
+    def owned_interior(self):
+        """global interior x rows owned by this slab: (first, count)"""
+        d = self.w.devinfo()
+        return d.li0 - self.w.nxb, d.nli
+
+    def _shot(self, phase, sx, sz, gz, dobs_all=None, is_=0):
+        L, h = self.L, self.h
+        ns = 1
+        ptr = None
+        if dobs_all is not None:
+            dobs_all = np.ascontiguousarray(dobs_all, np.float32)
+            ns = dobs_all.size // (self.w.nx * self.w.nt)
+            ptr = dobs_all.ctypes.data_as(C.c_void_p)
+        _lib.check(L, L.fdw_shot_begin(h, phase, sx, sz, gz, ptr, ns, is_))
+        self._levels(0, self.w.nt)
+
+    def model_shot(self, sx, sz, gz):
+        """one shot of mod_main (mod_main.cpp:141-169) on the slab-decomposed grid; returns this
+        slab's traces [nli][nt] (rows owned_interior())"""
+        self._shot(_lib.PHASE_MODEL, sx, sz, gz)
+        out = np.zeros((max(self.owned_interior()[1], 0), self.w.nt), np.float32)
+        _lib.check(self.L, self.L.fdw_shot_end(self.h, out if out.size else np.zeros(1, np.float32)))
+        return out
+
+    def rtm_shot_cpu(self, sx, sz, gz, dobs_all, is_=0):
+        """one shot of rtm_main (rtm_main.cpp:158-240) on the slab-decomposed grid: the forward
+        history is sharded with the slabs (each GPU keeps its own rows in HBM); returns this
+        slab's image rows [nli][nz]"""
+        self._shot(_lib.PHASE_RTM_FWD, sx, sz, gz)
+        self._shot(_lib.PHASE_RTM_BWD, sx, sz, gz, dobs_all, is_)
+        out = np.zeros((max(self.owned_interior()[1], 0), self.w.nz), np.float32)
+        _lib.check(self.L, self.L.fdw_shot_end(self.h, out if out.size else np.zeros(1, np.float32)))
+        return out
+
+    def gather_rows(self, local_rows):
+        """concatenate the per-slab row blocks on every rank (seismograms, images)"""
+        if self.world == 1:
+            return local_rows
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, local_rows)
+        return np.concatenate([p for p in parts if p.shape[0] > 0])
+
     # -- time stepping
     def advance(self, it0, nsteps):
         if self.world == 1:
             self.w.advance(it0, nsteps)
             return
-        import torch.distributed as dist
+        _lib.check(self.L, self.L.fdw_shot_begin(self.h, _lib.PHASE_PLAIN, 0, 0, 0, None, 1, 0))
+        self._levels(it0, nsteps)
+
+    def _levels(self, it0, nsteps):
+        """nsteps time levels of the current phase with the overlapped halo exchange"""
         L, h = self.L, self.h
+        if self.world == 1:
+            for it in range(it0, it0 + nsteps):
+                _lib.check(L, L.fdw_step_begin(h, it))
+                _lib.check(L, L.fdw_step_rows(h, 0, self.nloc, None))
+                _lib.check(L, L.fdw_step_end(h))
+            return
+        import torch.distributed as dist
         lo_nb, hi_nb = self.rank > 0, self.rank < self.world - 1
         ilo = GUARD if lo_nb else 0
         ihi = self.nloc - GUARD if hi_nb else self.nloc
@@ -213,3 +271,53 @@ def reduce_image(img, op="ordered"):
     for q in parts[1:]:
         acc += q
     return acc.cpu().numpy()
+
+
+def stack_images_chain(shot_images, shape):
+    """Bit-reproducible image stack for shot parallelism with contiguous shot blocks.
+
+    The reference stacks sequentially, img += imloc in shot order (fd-code.cu:525,
+    rtm_main.cpp:237).  Float addition is not associative, so per-rank partial sums followed by
+    a reduction give a different rounding.  Here the running sum travels down the ranks: rank r
+    receives the stack of all earlier shots, adds its own shot images in order and passes it
+    on; the last rank broadcasts the result.  Same additions in the same order as one process."""
+    import torch
+    import torch.distributed as dist
+    acc = np.zeros(shape, np.float32)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        for im in shot_images:
+            acc += im
+        return acc
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.zeros(shape, dtype=torch.float32, device=dev)
+    if rank > 0:
+        dist.recv(t, rank - 1)
+    for im in shot_images:
+        t += torch.from_numpy(np.ascontiguousarray(im, np.float32)).to(dev)
+    if rank < world - 1:
+        dist.send(t, rank + 1)
+    dist.broadcast(t, world - 1)
+    return t.cpu().numpy()
+
+
+def migrate_shots_gpu_family(wave, shots, v2_of_shot, dobs_of_shot, sx_of_shot, sz, gz, stack="chain"):
+    """Shot-parallel RTM with the GPU family's algorithm (main() loop of fd-code.cu:480-529):
+    this rank migrates `shots` (from shot_partition) on its own GPU -- forward with the two
+    saved levels left in HBM, time-reversed reconstruction + receiver back-propagation +
+    imaging -- and the per-shot images are stacked across ranks.
+
+    stack = "chain": bit-identical to the sequential reference order (needs contiguous blocks);
+            "allreduce": per-rank partial sums + one all-reduce (fast path)."""
+    images = []
+    for is_ in shots:
+        wave.set_v2(v2_of_shot(is_))
+        wave.forward(sx_of_shot(is_), sz, download=False)
+        images.append(wave.backward(dobs_of_shot(is_), gz))
+    shape = (wave.nx, wave.nz)
+    if stack == "chain":
+        return stack_images_chain(images, shape)
+    part = np.zeros(shape, np.float32)
+    for im in images:
+        part += im
+    return reduce_image(part, "allreduce")

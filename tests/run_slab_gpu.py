@@ -61,9 +61,77 @@ def main():
         ok = np.array_equal(newest.view(np.uint32), a.view(np.uint32)) and \
             np.array_equal(older.view(np.uint32), b.view(np.uint32))
         print("slab x%d vs single domain bitwise: %s" % (world, "OK" if ok else "MISMATCH"), flush=True)
+    ok = check_domain_divided_cpu_family(rank, world, lrank) and ok
+    ok = check_shot_parallel(rank, world, lrank) and ok
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
+
+
+def check_domain_divided_cpu_family(rank, world, lrank):
+    """config 5: mod_main + rtm_main algorithm, slab-decomposed over the GPUs (history sharded),
+    vs the same shot on one GPU: seismogram and image bit for bit."""
+    nx, nz, nb, nt = 1500, 700, 40, 120
+    nxe, nze = nx + 2 * nb, nz + 2 * nb
+    ve = np.empty((nxe, nze), np.float32)
+    ve[:, : nze // 2] = 2100.0
+    ve[:, nze // 2:] = 3300.0
+    v2 = ve * ve
+    srce = fdw.host.ricker_wavelet(nt, 0.001, 30.0, fdw.FAMILY_CPU)
+    sx, sz, gz = nb + nx // 2 - 3, nb, nb
+    kw = dict(order=8, fac=0.01, family=fdw.FAMILY_CPU, nt=nt)
+    sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, rank=rank, world=world, device=lrank,
+                          taper=fdw.TAPER_FOUR, **kw)
+    sp.set_stream(torch.cuda.current_stream().cuda_stream)
+    x0, x1 = sp.slab
+    sp.set_v2_local(v2[x0:x1]); sp.set_wavelet(srce)
+    data = sp.gather_rows(sp.model_shot(sx, sz, gz))
+    sp.close()
+    sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, rank=rank, world=world, device=lrank,
+                          taper=fdw.TAPER_TOP, history=True, **kw)
+    sp.set_stream(torch.cuda.current_stream().cuda_stream)
+    sp.set_v2_local(v2[x0:x1]); sp.set_wavelet(srce)
+    img = sp.gather_rows(sp.rtm_shot_cpu(sx, sz, gz, data[None], 0))
+    sp.close()
+    ok = True
+    if rank == 0:
+        with fdw.Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, taper=fdw.TAPER_FOUR, device=lrank, **kw) as w:
+            w.set_v2(v2); w.set_wavelet(srce)
+            d1 = w.model_shot(sx, sz, gz)
+        with fdw.Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, taper=fdw.TAPER_TOP, device=lrank, history=True, **kw) as w:
+            w.set_v2(v2); w.set_wavelet(srce)
+            i1 = w.rtm_shot_cpu(sx, sz, gz, d1[None], 0)
+        ok = np.array_equal(data.view(np.uint32), d1.view(np.uint32)) and np.array_equal(img.view(np.uint32), i1.view(np.uint32))
+        print("domain-divided mod_main+rtm_main x%d vs one GPU bitwise: %s (|img|max %.3g)" % (
+            world, "OK" if ok else "MISMATCH", np.abs(i1).max()), flush=True)
+    return ok
+
+
+def check_shot_parallel(rank, world, lrank):
+    """config 4 (small): shot-parallel GPU-family RTM with the chained stack vs the sequential loop."""
+    nx, nz, nb, nt, ns = 300, 200, 40, 150, 2 * world + 1
+    nxe, nze = nx + 2 * nb, nz + 2 * nb
+    rng = np.random.default_rng(5)
+    ve = np.full((nxe, nze), 2500.0, np.float32)
+    ve[:, nze // 2:] = 3500.0
+    v2 = ve * ve
+    dobs = rng.standard_normal((ns, nx, nt)).astype(np.float32)
+    srce = fdw.host.ricker_wavelet(nt, 0.001, 25.0, fdw.FAMILY_GPU)
+    kw = dict(order=8, fac=0.75, family=fdw.FAMILY_GPU, taper=fdw.TAPER_TOP, compat_extents=True, nt=nt, device=lrank)
+    with fdw.Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, **kw) as w:
+        w.set_wavelet(srce)
+        shots = D.shot_partition(ns, world, rank, contiguous=True)
+        img = D.migrate_shots_gpu_family(w, shots, lambda k: v2, lambda k: dobs[k], lambda k: nb + 10 + 20 * k, nb, nb)
+        ok = True
+        if rank == 0:
+            seq = np.zeros((nx, nz), np.float32)
+            for k in range(ns):
+                w.set_v2(v2)
+                w.forward(nb + 10 + 20 * k, nb, download=False)
+                seq += w.backward(dobs[k], nb)
+            ok = np.array_equal(img.view(np.uint32), seq.view(np.uint32))
+            print("shot-parallel x%d chained stack vs sequential bitwise: %s" % (world, "OK" if ok else "MISMATCH"), flush=True)
+    return ok
 
 
 if __name__ == "__main__":
