@@ -58,7 +58,7 @@ def c1_laplacian(device):
 
 
 def c4_rtm_shots(device, rank, world):
-    nx, nz, nb, nt = 8192, 4096, 40, int(os.environ.get("FDW_C4_NT", "150"))
+    nx, nz, nb, nt = 8192, 4096, 40, int(os.environ.get("FDW_C4_NT", "400"))
     ns = int(os.environ.get("FDW_C4_SHOTS", str(2 * world)))
     nxe, nze = nx + 2 * nb, nz + 2 * nb
     v2 = layered(nxe, nze)
@@ -71,6 +71,13 @@ def c4_rtm_shots(device, rank, world):
         w.set_v2(v2)
         w.forward(64, nb, download=False)  # warm-up
         w.backward(dobs, nb)
+        # breakdown of one shot (device work vs host transfers through pageable memory)
+        t0 = time.perf_counter(); w.set_v2(v2); t1 = time.perf_counter()
+        w.forward(64, nb, download=False); w.sync(); t2 = time.perf_counter()
+        w.backward(dobs, nb); t3 = time.perf_counter()
+        breakdown = {"set_v2_s": t1 - t0, "forward_s": t2 - t1, "backward_incl_traces_up_image_down_s": t3 - t2,
+                     "forward_gpts_per_s": nt * nxe * nze / (t2 - t1) / 1e9,
+                     "backward_gpts_per_s": 2.0 * nt * nxe * nze / (t3 - t2) / 1e9}
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
@@ -88,7 +95,7 @@ def c4_rtm_shots(device, rank, world):
     return {"config": "C4 multi-shot RTM 8192x4096 (+40 border), GPU-family algorithm, %d shots x %d steps on %d GPU(s), "
                       "shot-parallel; per shot: v2 upload, forward, backward+imaging, image download; final image "
                       "stack" % (ns, nt, world),
-            "seconds": dt, "gpts_per_s": upd / dt / 1e9, "updates": upd, "image_abs_max": float(np.abs(img).max())}
+            "seconds": dt, "gpts_per_s": upd / dt / 1e9, "updates": upd, "one_shot_breakdown": breakdown}
 
 
 def c5_cpu_family(device):

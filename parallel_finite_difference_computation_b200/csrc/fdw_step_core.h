@@ -335,7 +335,8 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
 }
 
 /* stand-alone Laplacian (config 1; kernel_lap fd-source-code.cu:110-135): the
- * exact reference sequence including the leading "0 +" adds; ring written 0. */
+ * exact reference sequence including the leading "0 +" adds; ring written 0.
+ * Same streaming structure and the same lean loop as step_thread. */
 template <int ORDER>
 FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, int bdim)
 {
@@ -347,29 +348,23 @@ FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, i
     const int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
     if (rb >= re) return;
     const long long pitch = a.pitch;
-    unsigned mlap = 0;
-    FDW_UNROLL
-    for (int k = 0; k < 4; k++)
-        if (j0 + k >= a.lap_j0 && j0 + k < a.lap_j1) mlap |= 1u << k;
-    const float *pc = a.p + j0 + (long long)(rb - H) * pitch;
-    float *out = lap + j0 + (long long)rb * pitch;
+    const bool ring = j0 < a.lap_j0 || j0 + 4 > a.lap_j1 || a.grow0 + rb < a.lap_i0 || a.grow0 + re > a.lap_i1;
+    const float *__restrict__ pc = a.p + j0 + (long long)(rb - H) * pitch;
+    float *__restrict__ out = lap + j0 + (long long)rb * pitch;
     float4 w[W];
     FDW_UNROLL
     for (int s = 0; s < 2 * H; s++) {
         w[s] = ld4(pc);
         pc += pitch;
     }
-    for (int r = rb; r < re; r += W) {
+    for (int left = re - rb; left > 0; left -= W) {
         FDW_UNROLL
         for (int u = 0; u < W; u++) {
-            const int lr = r + u;
-            if (lr < re) {
-                const int gi = a.grow0 + lr;
+            if (u < left) {
                 w[(u + 2 * H) % W] = ld4(pc);
                 const float *ctr = pc - (long long)H * pitch;
                 const float4 l4 = ld4(ctr - 4), r4 = ld4(ctr + 4), c4 = w[(u + H) % W];
                 const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
-                const unsigned ml = (gi >= a.lap_i0 && gi < a.lap_i1) ? mlap : 0u;
                 float res[4];
                 FDW_UNROLL
                 for (int k = 0; k < 4; k++) {
@@ -379,7 +374,14 @@ FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, i
                         az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
                         ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
                     }
-                    res[k] = ((ml >> k) & 1u) ? fadd(az, ax) : 0.0f;
+                    res[k] = fadd(az, ax);
+                }
+                if (ring) {
+                    const int gi = a.grow0 + re - left + u;
+                    const bool row_in = gi >= a.lap_i0 && gi < a.lap_i1;
+                    FDW_UNROLL
+                    for (int k = 0; k < 4; k++)
+                        if (!row_in || j0 + k < a.lap_j0 || j0 + k >= a.lap_j1) res[k] = 0.0f;
                 }
                 st4(out, make_float4(res[0], res[1], res[2], res[3]));
                 pc += pitch;
