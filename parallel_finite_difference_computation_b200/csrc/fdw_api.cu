@@ -31,6 +31,7 @@
 
 using fdw::GUARD;
 using fdw::StepArgs;
+using fdw::PersistArgs;
 
 /* ------------------------------------------------------------------ errors */
 static thread_local char g_err[512] = "";
@@ -93,6 +94,12 @@ struct fdw_ctx {
     bool saved_valid = false;
     int rows_per_cta_override = 0, threads_override = 0;
     long long small_grid_limit = 1LL << 18, fork_limit = 1LL << 20; /* in float4 columns x rows */
+    float *wavelet_d = nullptr; /* device copy of the wavelet (persistent kernel) */
+    unsigned *barrier_d = nullptr;
+    int *errflag_d = nullptr;
+    int coop = 0;                      /* device supports cooperative launches */
+    long long persist_limit = 1LL << 18; /* float4 columns x rows below which phases run persistently */
+    long long persist_launches = 0;
     int li0 = 0, nli = 0; /* interior x rows owned by this slab: global rows [li0, li0+nli) */
     /* split-phase shot state (slab decomposition) */
     int phase = 0, shot_gz = 0, shot_is = 0, shot_ns = 1;
@@ -150,6 +157,17 @@ static const void *step_kernel(int order, int recipe, int epi, int sponge)
     case 4: return fdw_step_kernel_o4(recipe, epi, sponge);
     case 6: return fdw_step_kernel_o6(recipe, epi, sponge);
     case 8: return fdw_step_kernel_o8(recipe, epi, sponge);
+    }
+    return nullptr;
+}
+
+static const void *persist_kernel(int order, int recipe, int epi)
+{
+    switch (order) {
+    case 2: return fdw_persist_kernel_o2(recipe, epi);
+    case 4: return fdw_persist_kernel_o4(recipe, epi);
+    case 6: return fdw_persist_kernel_o6(recipe, epi);
+    case 8: return fdw_persist_kernel_o8(recipe, epi);
     }
     return nullptr;
 }
@@ -346,6 +364,101 @@ static int step_pair(fdw_ctx *c, int pair, int recipe, int epi, bool sponge, boo
     return FDW_OK;
 }
 
+/* host copy of the per-level bookkeeping step_pair does, for n levels at once */
+static void replay_bookkeeping(fdw_ctx *c, int n, bool tap)
+{
+    for (int l = 0; l < n; l++) {
+        Field &nw = c->f[c->newest[0]], &ol = c->f[c->older[0]];
+        if (tap && c->prm.family == FDW_FAMILY_GPU) { nw.pend++; ol.pend++; }
+        ol.pend = 0;
+        if (tap && c->prm.family == FDW_FAMILY_CPU) { ol.pend = 1; nw.pend++; }
+        int t = c->newest[0];
+        c->newest[0] = c->older[0];
+        c->older[0] = t;
+    }
+}
+
+/* Try to run n consecutive levels of pair 0 in ONE cooperative launch (small, launch-bound
+ * grids).  Returns 1 when it did, 0 when the caller must fall back to per-level launches. */
+template <class Fill>
+static int try_persistent(fdw_ctx *c, int recipe, int epi, bool sponge, bool source, int it0, int n, int tidx_cpu,
+                          Fill fill, int *rc)
+{
+    *rc = FDW_OK;
+    if (!c->coop || n < 2 || c->gx0 != 0 || c->nloc != c->nxe || c->step_open) return 0;
+    const void *k = persist_kernel(c->prm.order, recipe, epi);
+    if (!k) return 0;
+    StepArgs base;
+    base_args(c, 0, &base);
+    const int rows = base.row1 - base.row0, nc = base.ncol4;
+    if (rows <= 0 || nc <= 0 || (long long)nc * rows >= c->persist_limit) return 0;
+    if (source && (it0 < 0 || (size_t)(it0 + n) > c->wavelet.size() || !c->wavelet_d)) return 0;
+    int nthreads = nc >= 256 ? 256 : ((nc + 31) / 32) * 32;
+    if (c->threads_override > 0) nthreads = c->threads_override;
+    const int gx = (nc + nthreads - 1) / nthreads;
+    const long long cap = (long long)c->nsm * cached_occupancy(k, nthreads);
+    int rpc = 2;
+    while ((long long)gx * ((rows + rpc - 1) / rpc) > cap && rpc < rows) rpc *= 2;
+    if ((long long)gx * ((rows + rpc - 1) / rpc) > cap) return 0;
+    const bool tap = sponge && c->prm.taper != FDW_TAPER_NONE;
+    PersistArgs pa;
+    memset(&pa, 0, sizeof pa);
+    base.taper_on = 1; /* the sponge instantiation serves every CTA; counts of 0 make it a no-op */
+    base.rows_per_cta = rpc;
+    if (source) { set_source_args(c, &base, it0); base.src_on = 1; }
+    fill(base);
+    pa.base = base;
+    pa.bufN = c->f[c->newest[0]].r0; pa.bufO = c->f[c->older[0]].r0;
+    pa.pendN = c->f[c->newest[0]].pend; pa.pendO = c->f[c->older[0]].pend;
+    pa.nlevels = n; pa.it0 = it0; pa.nt = c->prm.nt;
+    pa.sponge = tap ? 1 : 0;
+    pa.sponge_first = c->prm.family == FDW_FAMILY_GPU ? 1 : 0;
+    pa.source = source ? 1 : 0;
+    pa.tidx_cpu = tidx_cpu;
+    pa.wavelet = c->wavelet_d;
+    pa.hist = c->hist;
+    pa.hist_slice = (long long)(c->nli > 0 ? c->nli : 1) * c->pitch;
+    pa.barrier = c->barrier_d;
+    pa.error_flag = c->errflag_d;
+    if (cudaMemsetAsync(c->barrier_d, 0, sizeof(unsigned), c->stream) != cudaSuccess) return 0;
+    dim3 grid(gx, (rows + rpc - 1) / rpc, 1), block(nthreads, 1, 1);
+    void *params[] = {&pa};
+#ifdef FDW_EMU
+    emu_levels = n;
+#endif
+    cudaError_t e = cudaLaunchCooperativeKernel(k, grid, block, params, 0, c->stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError(); /* e.g. grid too large to be co-resident: fall back */
+        return 0;
+    }
+    c->launches++;
+    c->persist_launches++;
+    replay_bookkeeping(c, n, tap);
+    return 1;
+}
+
+/* n levels of pair 0: one persistent launch when the grid is small, else one launch per level */
+template <class FillStatic, class FillLevel>
+static int run_levels(fdw_ctx *c, int recipe, int epi, bool sponge, bool source, int it0, int n, int tidx_cpu,
+                      FillStatic fill_static, FillLevel fill_level)
+{
+    int rc;
+    if (try_persistent(c, recipe, epi, sponge, source, it0, n, tidx_cpu, fill_static, &rc)) return rc;
+    for (int it = it0; it < it0 + n; it++)
+        CHECK(step_pair(c, 0, recipe, epi, sponge, source, it, [&](StepArgs &a) { fill_level(a, it); }));
+    return FDW_OK;
+}
+
+static int check_device_flag(fdw_ctx *c)
+{
+    if (c->persist_launches == 0) return FDW_OK;
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, c->errflag_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (flag) { fdw_set_error("persistent kernel: grid barrier timed out"); return FDW_ERR_CUDA; }
+    return FDW_OK;
+}
+
 static int materialize(fdw_ctx *c, Field &f)
 {
     if (f.pend == 0) return FDW_OK;
@@ -492,6 +605,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_ROWS_PER_CTA")) c->rows_per_cta_override = atoi(e);
     if (const char *e = getenv("FDW_THREADS")) c->threads_override = atoi(e);
     if (const char *e = getenv("FDW_SMALL_GRID_LIMIT")) c->small_grid_limit = atoll(e);
+    if (const char *e = getenv("FDW_PERSIST_LIMIT")) c->persist_limit = atoll(e);
+    cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
 
     /* coefficients and scalars: fd-code.cu:203-217 / fd.c:12-16 */
@@ -565,6 +680,9 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
         if (prm->nt < 1) { fdw_destroy(c); fdw_set_error("fdw_create: history needs nt"); return FDW_ERR_ARG; }
         TRY(cudaMalloc(&c->hist, (size_t)prm->nt * img_elems * sizeof(float)));
     }
+    TRY(cudaMalloc(&c->barrier_d, sizeof(unsigned)));
+    TRY(cudaMalloc(&c->errflag_d, sizeof(int)));
+    TRY(cudaMemsetAsync(c->errflag_d, 0, sizeof(int), c->stream));
     TRY(cudaStreamSynchronize(c->stream)); /* the staging vectors go out of scope */
 #undef TRY
     *out = c;
@@ -579,6 +697,7 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     for (int k = 0; k < 4; k++) cudaFree(c->f[k].base);
     cudaFree(c->vdt_base); cudaFree(c->tz_base); cudaFree(c->tx_base);
     cudaFree(c->hist); cudaFree(c->img); cudaFree(c->dobs_d); cudaFree(c->rec_d);
+    cudaFree(c->wavelet_d); cudaFree(c->barrier_d); cudaFree(c->errflag_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -608,7 +727,7 @@ extern "C" int fdw_sync(fdw_ctx *c)
     if (!c) return FDW_ERR_ARG;
     CHECK(bind(c));
     CU(cudaStreamSynchronize(c->stream));
-    return FDW_OK;
+    return check_device_flag(c);
 }
 
 extern "C" int fdw_set_v2(fdw_ctx *c, const float *v2)
@@ -630,6 +749,12 @@ extern "C" int fdw_set_wavelet(fdw_ctx *c, const float *s, int nt)
 {
     if (!c || !s || nt < 0) return FDW_ERR_ARG;
     c->wavelet.assign(s, s + nt);
+    CHECK(bind(c));
+    if (c->wavelet_d) { cudaFree(c->wavelet_d); c->wavelet_d = nullptr; }
+    if (nt > 0) {
+        CU(cudaMalloc(&c->wavelet_d, (size_t)nt * sizeof(float)));
+        CU(cudaMemcpyAsync(c->wavelet_d, c->wavelet.data(), (size_t)nt * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
     return FDW_OK;
 }
 
@@ -669,16 +794,15 @@ extern "C" int fdw_fields_download(fdw_ctx *c, int pair, float *newest, float *o
     if (newest) { CHECK(materialize(c, n)); CHECK(field_d2h(c, n.r0, newest)); }
     if (older) { CHECK(materialize(c, o)); CHECK(field_d2h(c, o.r0, older)); }
     CU(cudaStreamSynchronize(c->stream));
-    return FDW_OK;
+    return check_device_flag(c);
 }
 
 extern "C" int fdw_advance(fdw_ctx *c, int it0, int nsteps)
 {
     if (!c || nsteps < 0) return FDW_ERR_ARG;
     CHECK(bind(c));
-    for (int it = it0; it < it0 + nsteps; it++)
-        CHECK(step_pair(c, 0, c->prm.recipe, 0, true, !c->wavelet.empty(), it, [](StepArgs &) {}));
-    return FDW_OK;
+    return run_levels(c, c->prm.recipe, 0, true, !c->wavelet.empty(), it0, nsteps, 0, [](StepArgs &) {},
+                      [](StepArgs &, int) {});
 }
 
 extern "C" int fdw_propagate(fdw_ctx *c, float *newest, float *older, int it0, int nsteps)
@@ -719,6 +843,8 @@ static int ensure_buffer(float **buf, size_t *cap, size_t need)
     return FDW_OK;
 }
 
+static int check_device_flag(fdw_ctx *c);
+
 static int image_download(fdw_ctx *c, float *imloc)
 {
     const fdw_params &p = c->prm;
@@ -726,7 +852,7 @@ static int image_download(fdw_ctx *c, float *imloc)
         CU(cudaMemcpy2DAsync(imloc, (size_t)p.nz * sizeof(float), c->img + p.nzb, c->pitch * sizeof(float),
                              (size_t)p.nz * sizeof(float), c->nli, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    return FDW_OK;
+    return check_device_flag(c);
 }
 
 extern "C" int fdw_backward(fdw_ctx *c, const float *P, const float *PP, const float *dobs, int gz, float *imloc)
@@ -845,10 +971,9 @@ static int phase_run(fdw_ctx *c, int phase)
 {
     const int nt = c->prm.nt;
     const bool source = phase != PHASE_RTM_BWD;
-    for (int it = 0; it < nt; it++)
-        CHECK(step_pair(c, 0, c->prm.recipe, phase_epi(phase), true, source, it,
-                        [&](StepArgs &a) { phase_fill(c, phase, it, a); }));
-    return FDW_OK;
+    return run_levels(c, c->prm.recipe, phase_epi(phase), true, source, 0, nt, phase == PHASE_RTM_BWD ? 1 : 0,
+                      [&](StepArgs &a) { phase_fill(c, phase, 0, a); },
+                      [&](StepArgs &a, int it) { phase_fill(c, phase, it, a); });
 }
 
 extern "C" int fdw_model_shot(fdw_ctx *c, int sx, int sz, int gz, float *data)

@@ -90,6 +90,74 @@ struct StepArgs {
     const float *img_field; /* EPI_IMG_FIELD: reconstructed source level, field layout */
 };
 
+/* the few quantities that change from one time level to the next; the ordinary kernels copy
+ * them out of StepArgs, the persistent multi-level kernel computes them per level */
+struct Level {
+    const float *p;
+    float *pp;
+    int np, no;
+    int src_on;
+    float src_amp;
+    int rec_it, inj_tidx;
+    float *hist_w;
+    const float *hist_r;
+    const float *img_field;
+};
+
+FDW_HD Level level_of(const StepArgs &a)
+{
+    Level lv;
+    lv.p = a.p; lv.pp = a.pp; lv.np = a.np; lv.no = a.no; lv.src_on = a.src_on; lv.src_amp = a.src_amp;
+    lv.rec_it = a.rec_it; lv.inj_tidx = a.inj_tidx; lv.hist_w = a.hist_w; lv.hist_r = a.hist_r;
+    lv.img_field = a.img_field;
+    return lv;
+}
+
+/* arguments of the persistent kernel: `nlevels` consecutive time levels of ONE propagation in one
+ * cooperative launch, a grid-wide barrier between levels (launch-bound small grids) */
+struct PersistArgs {
+    StepArgs base;
+    float *bufN, *bufO; /* newest / older level at entry */
+    int pendN, pendO;   /* their pending sponge counts at entry */
+    int nlevels, it0, nt;
+    int sponge;         /* 1: the context's sponge is active in this phase */
+    int sponge_first;   /* 1: GPU-family order (sponge, update); 0: CPU-family order (update, sponge) */
+    int source;         /* 1: add wavelet[it] at the source */
+    int tidx_cpu;       /* back-injection sample: 0 -> nt-1-it (fd-code.cu:129), 1 -> nt-it (rtm_main.cpp:202) */
+    const float *wavelet;
+    float *hist;        /* forward history base, slices of hist_slice floats */
+    long long hist_slice;
+    unsigned *barrier;  /* zeroed before the launch */
+    int *error_flag;
+};
+
+/* the Level of launch-relative level l, in closed form (see the host bookkeeping in step_pair) */
+FDW_HD Level persist_level_of(const PersistArgs &pa, int l)
+{
+    Level lv;
+    const int it = pa.it0 + l;
+    lv.p = (l & 1) ? pa.bufO : pa.bufN;
+    lv.pp = (l & 1) ? pa.bufN : pa.bufO;
+    if (!pa.sponge) {
+        lv.np = l == 0 ? pa.pendN : 0;
+        lv.no = l == 0 ? pa.pendO : (l == 1 ? pa.pendN : 0);
+    } else if (pa.sponge_first) {
+        lv.np = l == 0 ? pa.pendN + 1 : 1;
+        lv.no = l == 0 ? pa.pendO + 1 : (l == 1 ? pa.pendN + 2 : 2);
+    } else {
+        lv.np = l == 0 ? pa.pendN : 1;
+        lv.no = l == 0 ? pa.pendO : (l == 1 ? pa.pendN + 1 : 2);
+    }
+    lv.src_on = pa.source;
+    lv.src_amp = pa.source ? pa.wavelet[it] : 0.0f;
+    lv.rec_it = it;
+    lv.inj_tidx = pa.tidx_cpu ? pa.nt - it : pa.nt - 1 - it;
+    lv.hist_w = pa.hist ? pa.hist + (long long)it * pa.hist_slice : nullptr;
+    lv.hist_r = pa.hist ? pa.hist + (long long)(pa.nt - 1 - it) * pa.hist_slice : nullptr;
+    lv.img_field = nullptr;
+    return lv;
+}
+
 FDW_HD float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 FDW_HD void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
@@ -143,14 +211,14 @@ static __host__ __device__ __noinline__
 #else
 static
 #endif
-float4 add_source(const StepArgs &a, float4 r4, int gi, int j0)
+float4 add_source(const StepArgs &a, float src_amp, float4 r4, int gi, int j0)
 {
     float res[4] = {r4.x, r4.y, r4.z, r4.w};
     const int di = gi - a.src_gi;
     for (int k = 0; k < 4; k++) {
         const int dj = j0 + k - a.src_j;
         if (dj >= -a.src_rad && dj <= a.src_rad && j0 + k < a.nze) {
-            const float amp = a.src_rad ? fmul(a.src_amp, a.src_w[(di + 3) * 7 + (dj + 3)]) : a.src_amp;
+            const float amp = a.src_rad ? fmul(src_amp, a.src_w[(di + 3) * 7 + (dj + 3)]) : src_amp;
             res[k] = fadd(res[k], amp);
         }
     }
@@ -158,7 +226,7 @@ float4 add_source(const StepArgs &a, float4 r4, int gi, int j0)
 }
 
 template <int ORDER, int RECIPE, bool TAPER, int EPI>
-FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
+FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int tid, int bdim)
 {
     constexpr int H = ORDER / 2, W = ORDER + 1;
     const int q = a.col4_0 + bx * bdim + tid;
@@ -175,7 +243,7 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
      * every row).  ring: some of this thread's 4 columns, or some of this CTA's rows, lie where
      * the Laplacian is defined as 0.  near_src: the source patch overlaps these 4 columns. */
     const bool ring = j0 < a.lap_j0 || j0 + 4 > a.lap_j1 || a.grow0 + rb < a.lap_i0 || a.grow0 + re > a.lap_i1;
-    const bool near_src = a.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
+    const bool near_src = lv.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
 
     /* sponge factors of the 12 columns j0-4 .. j0+7 */
     float zf[12];
@@ -188,8 +256,8 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
         }
     }
 
-    const float *__restrict__ pc = a.p + j0 + (long long)(rb - H) * pitch; /* row being streamed in */
-    float *__restrict__ ppc = a.pp + j0 + (long long)rb * pitch;
+    const float *__restrict__ pc = lv.p + j0 + (long long)(rb - H) * pitch; /* row being streamed in */
+    float *__restrict__ ppc = lv.pp + j0 + (long long)rb * pitch;
     const float *__restrict__ vc = a.vdt + j0 + (long long)rb * pitch;
 
     float4 w[W];
@@ -198,7 +266,7 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
         w[s] = ld4(pc);
         if (TAPER) {
             int lr = rb - H + s;
-            w[s] = tap4(w[s], zf + 4, xon >> 4, a.tx[lr], a.grow0 + lr < a.tz_ilim, a.np);
+            w[s] = tap4(w[s], zf + 4, xon >> 4, a.tx[lr], a.grow0 + lr < a.tz_ilim, lv.np);
         }
         pc += pitch;
     }
@@ -218,10 +286,10 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                 if (TAPER) {
                     const float xf = a.tx[lr];
                     const bool zon = gi < a.tz_ilim;
-                    wn = tap4(wn, zf + 4, xon >> 4, a.tx[lr + H], gi + H < a.tz_ilim, a.np);
-                    l4 = tap4(l4, zf, xon, xf, zon, a.np);
-                    r4 = tap4(r4, zf + 8, xon >> 8, xf, zon, a.np);
-                    o4 = tap4(o4, zf + 4, xon >> 4, xf, zon, a.no);
+                    wn = tap4(wn, zf + 4, xon >> 4, a.tx[lr + H], gi + H < a.tz_ilim, lv.np);
+                    l4 = tap4(l4, zf, xon, xf, zon, lv.np);
+                    r4 = tap4(r4, zf + 8, xon >> 8, xf, zon, lv.np);
+                    o4 = tap4(o4, zf + 4, xon >> 4, xf, zon, lv.no);
                 }
                 w[(u + 2 * H) % W] = wn;
                 const float4 c4 = w[(u + H) % W];
@@ -281,13 +349,13 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
 
                 /* ---- source (after the update, before the sponge: both families) */
                 if (near_src && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad) {
-                    const float4 s4 = add_source(a, make_float4(res[0], res[1], res[2], res[3]), gi, j0);
+                    const float4 s4 = add_source(a, lv.src_amp, make_float4(res[0], res[1], res[2], res[3]), gi, j0);
                     res[0] = s4.x; res[1] = s4.y; res[2] = s4.z; res[3] = s4.w;
                 }
                 /* ---- receiver back-injection */
                 if ((EPI & EPI_INJECT) && gi >= a.inj_gi0 && gi < a.inj_gi0 + a.inj_n && a.inj_j >= j0 &&
                     a.inj_j < j0 + 4) {
-                    long long idx = a.dobs_base + (long long)(gi - a.inj_gi0) * a.inj_nt + a.inj_tidx;
+                    long long idx = a.dobs_base + (long long)(gi - a.inj_gi0) * a.inj_nt + lv.inj_tidx;
                     float s = (idx >= 0 && idx < a.dobs_len) ? a.dobs[idx] : 0.0f;
                     FDW_UNROLL
                     for (int k = 0; k < 4; k++)
@@ -300,15 +368,15 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                     a.rec_j < j0 + 4) {
                     float4 s4 = c4;
                     if (TAPER) s4 = tap4(s4, zf + 4, xon >> 4, a.tx[lr], gi < a.tz_ilim, 1);
-                    a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + a.rec_it] = getk(s4, a.rec_j - j0);
+                    a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = getk(s4, a.rec_j - j0);
                 }
                 /* ---- forward history: interior rows of the newer level (sponge factor there is 1) */
                 if ((EPI & EPI_HSTORE) && gi >= a.hist_gi0 && gi < a.hist_gi0 + a.hist_n)
-                    st4(a.hist_w + (long long)(gi - a.hist_gi0) * pitch + j0, c4);
+                    st4(lv.hist_w + (long long)(gi - a.hist_gi0) * pitch + j0, c4);
                 /* ---- imaging condition */
                 if ((EPI & EPI_IMG_HIST) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
                     float *ip = a.img + (long long)(gi - a.img_gi0) * pitch + j0;
-                    const float4 s4 = ld4_stream(a.hist_r + (long long)(gi - a.hist_gi0) * pitch + j0);
+                    const float4 s4 = ld4_stream(lv.hist_r + (long long)(gi - a.hist_gi0) * pitch + j0);
                     float4 im = ld4(ip);
                     im.x = fadd(im.x, fmul(s4.x, c4.x));
                     im.y = fadd(im.y, fmul(s4.y, c4.y));
@@ -318,7 +386,7 @@ FDW_HD void step_thread(const StepArgs &a, int bx, int by, int tid, int bdim)
                 }
                 if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
                     float *ip = a.img + (long long)(gi - a.img_gi0) * pitch + j0;
-                    const float4 s4 = ld4_stream(a.img_field + (long long)lr * pitch + j0);
+                    const float4 s4 = ld4_stream(lv.img_field + (long long)lr * pitch + j0);
                     float4 im = ld4(ip);
                     im.x = fadd(im.x, fmul(s4.x, res[0]));
                     im.y = fadd(im.y, fmul(s4.y, res[1]));

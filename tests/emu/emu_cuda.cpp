@@ -6,6 +6,7 @@
 
 thread_local uint3_emu blockIdx, threadIdx;
 thread_local dim3 blockDim, gridDim;
+int emu_level = 0, emu_levels = 0;
 
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
@@ -70,3 +71,14 @@ cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **arg
     }
     return cudaSuccess;
 }
+
+cudaError_t cudaLaunchCooperativeKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t st)
+{
+    for (int l = 0; l < emu_levels; l++) {
+        emu_level = l;
+        cudaLaunchKernel(func, grid, block, args, smem, st);
+    }
+    emu_level = 0;
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceGetAttribute(int *value, int, int) { *value = 1; return cudaSuccess; }

@@ -30,6 +30,8 @@ struct dim3 {
 struct uint3_emu { unsigned x, y, z; };
 extern thread_local uint3_emu blockIdx, threadIdx;
 extern thread_local dim3 blockDim, gridDim;
+extern int emu_level;  /* level index seen by the persistent kernel's host stand-in */
+extern int emu_levels; /* set by the caller before cudaLaunchCooperativeKernel */
 struct cudaDeviceProp { int multiProcessorCount; };
 
 #define __global__
@@ -63,4 +65,8 @@ cudaError_t cudaEventElapsedTime(float *, cudaEvent_t, cudaEvent_t);
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *, const void *, int, size_t);
 /* `func` is a thunk void(*)(void **args) executed once per emulated thread */
 cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t);
+/* runs the thunk emu_levels times, level by level (the grid barrier of the real kernel) */
+cudaError_t cudaLaunchCooperativeKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t);
+enum { cudaDevAttrCooperativeLaunch = 95 };
+cudaError_t cudaDeviceGetAttribute(int *value, int attr, int device);
 #endif

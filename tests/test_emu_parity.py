@@ -14,11 +14,13 @@ def emu():
     return load_emu()
 
 
-@pytest.fixture(params=["one-launch", "rectangles", "rectangles+fork"])
+@pytest.fixture(params=["persistent", "one-launch", "rectangles", "rectangles+fork"])
 def launch_mode(request, monkeypatch):
     """the library picks one sponge-kernel launch for tiny grids and plain/sponge rectangles
     (optionally forked to a side stream) for large ones; force each path on the small test grids"""
-    if request.param != "one-launch":
+    if request.param != "persistent":
+        monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")  # one launch per level
+    if request.param not in ("one-launch", "persistent"):
         monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
         monkeypatch.setenv("FDW_FORK_LIMIT", "0" if request.param.endswith("fork") else str(1 << 40))
     return request.param

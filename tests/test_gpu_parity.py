@@ -33,9 +33,11 @@ def test_stencil_golden_output_teste(lib, golden_dir):
     PC.case_stencil_golden(lib, golden_dir)
 
 
-@pytest.fixture(params=["one-launch", "rectangles+fork"])
+@pytest.fixture(params=["persistent", "one-launch", "rectangles+fork"])
 def launch_mode(request, monkeypatch):
-    if request.param != "one-launch":
+    if request.param != "persistent":
+        monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")  # one launch per level
+    if request.param not in ("one-launch", "persistent"):
         monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
         monkeypatch.setenv("FDW_FORK_LIMIT", "0")
     return request.param
