@@ -77,9 +77,73 @@ __global__ void __launch_bounds__(256,MINB) k(const __grid_constant__ Args a){
   }
 }
 
+
+// SHFL variant: z neighbours from the neighbouring lanes' centre-row registers; each warp computes 30 float4
+// columns (lanes 1..30), lanes 0 and 31 only carry the halo columns.  Fresh loads per row: wn, o, v -- all
+// consumed at the END of the row's arithmetic, so their latency overlaps the ~150 FP instructions before.
+template<int MINB, int NCHK>
+__global__ void __launch_bounds__(256,MINB) ks(const __grid_constant__ Args a){
+  constexpr int ORDER=8,H=4,W=9;
+  const int lane=threadIdx.x&31, warp=threadIdx.x>>5;
+  const int wpb=blockDim.x>>5;
+  const int q=(blockIdx.x*wpb+warp)*30+lane-1;        // float4 column, may be -1 or >= ncol4 on halo lanes
+  if((blockIdx.x*wpb+warp)*30>=a.ncol4) return;         // whole warp out of range
+  const bool comp = lane>=1 && lane<=30 && q<a.ncol4;
+  const int j0=q*4;
+  const int rb=a.row0+blockIdx.y*a.rows_per_cta; const int re=min(rb+a.rows_per_cta,a.row1); if(rb>=re) return;
+  const long long pitch=a.pitch;
+  const bool ring = j0<a.lap_j0 || j0+4>a.lap_j1 || rb<a.lap_i0 || re>a.lap_i1;
+  const bool near_src = a.src_on && a.src_j>=j0 && a.src_j<j0+4;
+  const float* __restrict__ pc=a.p+j0+(long long)(rb-H)*pitch;
+  float* __restrict__ ppc=a.pp+j0+(long long)rb*pitch;
+  const float* __restrict__ vc=a.vdt+j0+(long long)rb*pitch;
+  float4 w[W];
+  #pragma unroll
+  for(int s=0;s<2*H;s++){ w[s]=ld4(pc); pc+=pitch; }
+  for(int left=re-rb; left>0; left-=W){
+    #pragma unroll
+    for(int u=0;u<W;u++){
+      if(u<left){
+        float4 wn=ld4(pc);
+        float4 o=make_float4(0,0,0,0), v=o;
+        if(comp){ o=ld4(ppc); v=ldnc(vc); }
+        const float4 c4=w[(u+H)%W];
+        float4 l,r;
+        l.x=__shfl_up_sync(0xffffffffu,c4.x,1); l.y=__shfl_up_sync(0xffffffffu,c4.y,1); l.z=__shfl_up_sync(0xffffffffu,c4.z,1); l.w=__shfl_up_sync(0xffffffffu,c4.w,1);
+        r.x=__shfl_down_sync(0xffffffffu,c4.x,1); r.y=__shfl_down_sync(0xffffffffu,c4.y,1); r.z=__shfl_down_sync(0xffffffffu,c4.z,1); r.w=__shfl_down_sync(0xffffffffu,c4.w,1);
+        const float za[12]={l.x,l.y,l.z,l.w,c4.x,c4.y,c4.z,c4.w,r.x,r.y,r.z,r.w};
+        float lap[4];
+        #pragma unroll
+        for(int k2=0;k2<4;k2++){
+          float az=__fmul_rn(za[k2],a.cz[0]); float ax=__fmul_rn(getk(w[u%W],k2),a.cx[0]);
+          #pragma unroll
+          for(int io=1;io<ORDER;io++){ az=__fadd_rn(az,__fmul_rn(za[k2+io],a.cz[io])); ax=__fadd_rn(ax,__fmul_rn(getk(w[(u+io)%W],k2),a.cx[io])); }
+          az=__fadd_rn(az,__fmul_rn(za[k2+ORDER],a.cz[ORDER]));
+          ax=__fadd_rn(ax,__fmul_rn(getk(wn,k2),a.cx[ORDER]));     // the freshly loaded row is the LAST tap
+          lap[k2]=__fadd_rn(az,ax);
+        }
+        w[(u+2*H)%W]=wn;
+        if(ring){ const int lr=re-left+u; const bool rin=lr>=a.lap_i0&&lr<a.lap_i1;
+          #pragma unroll
+          for(int k2=0;k2<4;k2++) if(!rin||j0+k2<a.lap_j0||j0+k2>=a.lap_j1) lap[k2]=0.f; }
+        float res[4];
+        #pragma unroll
+        for(int k2=0;k2<4;k2++) res[k2]=leap(getk(c4,k2),getk(o,k2),__fmul_rn(getk(v,k2),lap[k2]));
+        if(near_src && re-left+u==a.src_gi){
+          #pragma unroll
+          for(int k2=0;k2<4;k2++) if(j0+k2==a.src_j) res[k2]=__fadd_rn(res[k2],a.src_amp);
+        }
+        if(comp) *reinterpret_cast<float4*>(ppc)=make_float4(res[0],res[1],res[2],res[3]);
+        pc+=pitch; ppc+=pitch; vc+=pitch;
+      }
+    }
+  }
+}
+
 typedef void (*kfn)(const Args);
-struct Var { const char* name; kfn f; int minb; };
-#define V(PF,HINT,MINB) {"PF" #PF "_H" #HINT "_B" #MINB, k<PF,HINT,MINB>, MINB}
+struct Var { const char* name; kfn f; int minb; int shfl; };
+#define V(PF,HINT,MINB) {"PF" #PF "_H" #HINT "_B" #MINB, k<PF,HINT,MINB>, MINB, 0}
+#define VS(MINB) {"SHFL_B" #MINB, ks<MINB,0>, MINB, 1}
 
 int main(int argc,char**argv){
   int n = argc>1?atoi(argv[1]):16384;
@@ -93,7 +157,7 @@ int main(int argc,char**argv){
   Args a; memset(&a,0,sizeof a); a.p=p+5*pitch; a.vdt=v+5*pitch; a.pitch=pitch; a.ncol4=(n+3)/4; a.row0=0;a.row1=n;
   a.lap_i0=4;a.lap_i1=n-4;a.lap_j0=4;a.lap_j1=n-4; a.src_on=1;a.src_gi=n/2;a.src_j=40;a.src_amp=0.5f;
   for(int i=0;i<9;i++){a.cz[i]=0.01f*(i+1)*(i%2?1:-1); a.cx[i]=0.02f*(9-i)*(i%2?-1:1);}
-  Var vars[]={V(0,0,2),V(0,0,3),V(0,0,4),V(1,0,2),V(1,0,3),V(1,0,4),V(0,1,3),V(1,1,2),V(1,1,3),V(1,1,4)};
+  Var vars[]={V(0,0,4),VS(4),VS(3),VS(5),V(0,0,3)};
   int nsm; cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,0);
   cudaEvent_t e0,e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   bool have_ref=false;
@@ -101,7 +165,7 @@ int main(int argc,char**argv){
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa,vr.f);
     for(int nt: {128,256}) for(int rpc: {16,32,64,128}){
       int occ=0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,vr.f,nt,0);
-      dim3 grid((a.ncol4+nt-1)/nt,(n+rpc-1)/rpc), block(nt); a.rows_per_cta=rpc;
+      int cols_per_blk = vr.shfl ? (nt/32)*30 : nt; dim3 grid((a.ncol4+cols_per_blk-1)/cols_per_blk,(n+rpc-1)/rpc), block(nt); a.rows_per_cta=rpc;
       float best=1e9;
       for(int rep=0;rep<4;rep++){
         cudaMemcpy(pp,pp0,elems*4,cudaMemcpyDeviceToDevice); a.pp=pp+5*pitch;
