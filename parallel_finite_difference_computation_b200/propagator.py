@@ -126,7 +126,7 @@ class Wave2D:
     def rtm_shot_cpu(self, sx, sz, gz, dobs_all, is_=0):
         """one shot of rtm_main (rtm_main.cpp:158-240) -> imloc [nx][nz]."""
         dobs_all = np.ascontiguousarray(dobs_all, np.float32)
-        ns = dobs_all.size // (self.nx * self.nt)
+        ns = dobs_all.size // (self.nx * self.nt) if self.nt > 0 else 1
         im = np.zeros((self.nx, self.nz), np.float32)
         self._ck(self.L.fdw_rtm_shot_cpu(self.h, sx, sz, gz, dobs_all.reshape(-1), ns, is_, im))
         return im

@@ -140,10 +140,69 @@ __global__ void __launch_bounds__(256,MINB) ks(const __grid_constant__ Args a){
   }
 }
 
+__device__ __forceinline__ void pf_l2(const void* p){ asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void pf_l1(const void* p){ asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+// lean loop + cache prefetch D rows ahead (no registers): LVL 2 = L2, 1 = L1
+template<int MINB,int D,int LVL>
+__global__ void __launch_bounds__(256,MINB) kp(const __grid_constant__ Args a){
+  constexpr int ORDER=8,H=4,W=9;
+  const int q=blockIdx.x*blockDim.x+threadIdx.x; if(q>=a.ncol4) return;
+  const int j0=q*4;
+  const int rb=a.row0+blockIdx.y*a.rows_per_cta; const int re=min(rb+a.rows_per_cta,a.row1); if(rb>=re) return;
+  const long long pitch=a.pitch;
+  const bool ring = j0<a.lap_j0 || j0+4>a.lap_j1 || rb<a.lap_i0 || re>a.lap_i1;
+  const bool near_src = a.src_on && a.src_j>=j0 && a.src_j<j0+4;
+  const bool pfl = (threadIdx.x & 7)==0;   // one lane per 128-byte line
+  const float* __restrict__ pc=a.p+j0+(long long)(rb-H)*pitch;
+  float* __restrict__ ppc=a.pp+j0+(long long)rb*pitch;
+  const float* __restrict__ vc=a.vdt+j0+(long long)rb*pitch;
+  float4 w[W];
+  #pragma unroll
+  for(int s=0;s<2*H;s++){ w[s]=ld4(pc); pc+=pitch; }
+  if(pfl){
+    #pragma unroll
+    for(int d=0;d<D;d++){ if(LVL==2){pf_l2(pc+d*pitch);pf_l2(ppc+d*pitch);pf_l2(vc+d*pitch);} else {pf_l1(pc+d*pitch);pf_l1(ppc+d*pitch);pf_l1(vc+d*pitch);} }
+  }
+  for(int left=re-rb; left>0; left-=W){
+    #pragma unroll
+    for(int u=0;u<W;u++){
+      if(u<left){
+        if(pfl){ if(LVL==2){pf_l2(pc+D*pitch);pf_l2(ppc+D*pitch);pf_l2(vc+D*pitch);} else {pf_l1(pc+D*pitch);pf_l1(ppc+D*pitch);pf_l1(vc+D*pitch);} }
+        w[(u+2*H)%W]=ld4(pc);
+        const float* ctr=pc-(long long)H*pitch;
+        const float4 l=ld4(ctr-4), r=ld4(ctr+4), o=ld4(ppc), v=ldnc(vc);
+        const float4 c4=w[(u+H)%W];
+        const float za[12]={l.x,l.y,l.z,l.w,c4.x,c4.y,c4.z,c4.w,r.x,r.y,r.z,r.w};
+        float lap[4];
+        #pragma unroll
+        for(int k2=0;k2<4;k2++){
+          float az=__fmul_rn(za[k2],a.cz[0]); float ax=__fmul_rn(getk(w[u%W],k2),a.cx[0]);
+          #pragma unroll
+          for(int io=1;io<=ORDER;io++){ az=__fadd_rn(az,__fmul_rn(za[k2+io],a.cz[io])); ax=__fadd_rn(ax,__fmul_rn(getk(w[(u+io)%W],k2),a.cx[io])); }
+          lap[k2]=__fadd_rn(az,ax);
+        }
+        if(ring){ const int lr=re-left+u; const bool rin=lr>=a.lap_i0&&lr<a.lap_i1;
+          #pragma unroll
+          for(int k2=0;k2<4;k2++) if(!rin||j0+k2<a.lap_j0||j0+k2>=a.lap_j1) lap[k2]=0.f; }
+        float res[4];
+        #pragma unroll
+        for(int k2=0;k2<4;k2++) res[k2]=leap(getk(c4,k2),getk(o,k2),__fmul_rn(getk(v,k2),lap[k2]));
+        if(near_src && re-left+u==a.src_gi){
+          #pragma unroll
+          for(int k2=0;k2<4;k2++) if(j0+k2==a.src_j) res[k2]=__fadd_rn(res[k2],a.src_amp);
+        }
+        *reinterpret_cast<float4*>(ppc)=make_float4(res[0],res[1],res[2],res[3]);
+        pc+=pitch; ppc+=pitch; vc+=pitch;
+      }
+    }
+  }
+}
+
 typedef void (*kfn)(const Args);
 struct Var { const char* name; kfn f; int minb; int shfl; };
 #define V(PF,HINT,MINB) {"PF" #PF "_H" #HINT "_B" #MINB, k<PF,HINT,MINB>, MINB, 0}
 #define VS(MINB) {"SHFL_B" #MINB, ks<MINB,0>, MINB, 1}
+#define VP(MINB,D,LVL) {"PFL" #LVL "_D" #D "_B" #MINB, kp<MINB,D,LVL>, MINB, 0}
 
 int main(int argc,char**argv){
   int n = argc>1?atoi(argv[1]):16384;
@@ -157,13 +216,13 @@ int main(int argc,char**argv){
   Args a; memset(&a,0,sizeof a); a.p=p+5*pitch; a.vdt=v+5*pitch; a.pitch=pitch; a.ncol4=(n+3)/4; a.row0=0;a.row1=n;
   a.lap_i0=4;a.lap_i1=n-4;a.lap_j0=4;a.lap_j1=n-4; a.src_on=1;a.src_gi=n/2;a.src_j=40;a.src_amp=0.5f;
   for(int i=0;i<9;i++){a.cz[i]=0.01f*(i+1)*(i%2?1:-1); a.cx[i]=0.02f*(9-i)*(i%2?-1:1);}
-  Var vars[]={V(0,0,4),VS(4),VS(3),VS(5),V(0,0,3)};
+  Var vars[]={VP(4,0,2),VP(4,4,2),VP(4,8,2),VP(4,16,2),VP(4,4,1),VP(4,8,1),VP(3,8,2)};
   int nsm; cudaDeviceGetAttribute(&nsm,cudaDevAttrMultiProcessorCount,0);
   cudaEvent_t e0,e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   bool have_ref=false;
   for(auto& vr:vars){
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa,vr.f);
-    for(int nt: {128,256}) for(int rpc: {16,32,64,128}){
+    for(int nt: {256}) for(int rpc: {32,64,128,148}){
       int occ=0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ,vr.f,nt,0);
       int cols_per_blk = vr.shfl ? (nt/32)*30 : nt; dim3 grid((a.ncol4+cols_per_blk-1)/cols_per_blk,(n+rpc-1)/rpc), block(nt); a.rows_per_cta=rpc;
       float best=1e9;
