@@ -38,6 +38,7 @@ DX = DZ = 10.0
 DT = 0.001
 FPEAK = 20.0
 FAC = 0.75
+HALO = os.environ.get("FDW_BENCH_HALO", "p2p")  # slab halo exchange at N>1: "p2p" (peer stores over NVLink) or "nccl"
 RECIPE = os.environ.get("FDW_BENCH_RECIPE", "G")  # "G" = bit-exact reference arithmetic (headline); "FAST" = FMA recipe
 BYTES_PER_POINT = 16  # read p, pp, v2*dt2 + write pp
 METRIC = "grid-point updates/sec"
@@ -182,6 +183,8 @@ def workload_config(ngpus):
                            "G (bit-exact)" if RECIPE != "FAST" else "FAST (FMA, tolerance-checked)", LEVELS),
             "grid": [NGRID * ngpus, NGRID], "levels_per_step": LEVELS, "order": 8, "recipe": RECIPE,
             "partition": "slab-x%d" % ngpus if ngpus > 1 else "single",
+            "halo_exchange": ("peer stores into the neighbour's ghost rows from the boundary kernel (CUDA IPC, "
+                              "NVLink), device-side flags" if HALO == "p2p" else "NCCL send/recv") if ngpus > 1 else None,
             "l2": "working set 3 GiB per GPU > 126 MB L2, no flush needed"}
 
 
@@ -211,7 +214,7 @@ def run_ours(args):
     srce = fdw.host.ricker_wavelet(10000, DT, FPEAK, fdw.FAMILY_GPU)
     prop = fdist.SlabPropagator(nx, nz, nb, nb, DX, DZ, DT, order=8, fac=FAC, family=fdw.FAMILY_GPU,
                                 recipe=fdw.RECIPE_FAST if RECIPE == "FAST" else fdw.RECIPE_G,
-                                taper=fdw.TAPER_TOP, device=local_rank, rank=rank, world=world)
+                                taper=fdw.TAPER_TOP, device=local_rank, rank=rank, world=world, halo=HALO)
     # a non-default torch stream: the library launches on it, and the torch events below time it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)

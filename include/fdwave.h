@@ -201,6 +201,34 @@ int fdw_set_v2_local(fdw_ctx *ctx, const float *v2_rows);
 int fdw_fields_upload_local(fdw_ctx *ctx, int pair, const float *newest, const float *older);
 int fdw_fields_download_local(fdw_ctx *ctx, int pair, float *newest, float *older);
 
+/* ---------------------------------------------------------------- peer-memory halo exchange
+ * (one process per GPU, NVLink / NVSwitch P2P; the reference has no multi-GPU path)
+ * Instead of handing the boundary rows to a communication library, neighbouring slab contexts
+ * map each other's buffers through CUDA IPC.  fdw_peer_levels then drives whole time levels:
+ * the boundary-strip launch writes its rows locally and into the neighbour's ghost rows in the
+ * same kernel, a release flag follows, the interior update overlaps the transfer and the next
+ * level's boundary launch waits (on the device) for the neighbours' flags.  Results are bit for
+ * bit those of fdw_step_begin/rows/end with any other exchange, and of the single domain.
+ *   fdw_peer_export    this slab's handles (send to both neighbours, e.g. all_gather)
+ *   fdw_peer_attach    map the lower / upper neighbour's buffers (NULL = grid edge)
+ *   fdw_peer_refresh   push the newest level's boundary rows (after an upload); all slabs call it
+ *   fdw_peer_levels    nsteps levels of the current phase (fdw_shot_begin), asynchronous
+ *   fdw_peer_fence     stream-side wait until every push addressed to this slab has landed;
+ *                      call before zeroing / uploading / downloading after fdw_peer_levels */
+#define FDW_IPC_HANDLE_BYTES 64
+typedef struct fdw_peer_info {
+    unsigned char field[4][FDW_IPC_HANDLE_BYTES];
+    unsigned char flags[FDW_IPC_HANDLE_BYTES];
+    long long pitch;
+    int nloc, gx0, device, reserved;
+} fdw_peer_info;
+int fdw_peer_export(fdw_ctx *ctx, fdw_peer_info *out);
+int fdw_peer_attach(fdw_ctx *ctx, const fdw_peer_info *lower, const fdw_peer_info *upper);
+int fdw_peer_detach(fdw_ctx *ctx);
+int fdw_peer_refresh(fdw_ctx *ctx);
+int fdw_peer_levels(fdw_ctx *ctx, int it0, int nsteps);
+int fdw_peer_fence(fdw_ctx *ctx);
+
 /* ---------------------------------------------------------------- device-resident access
  * (benchmarks / multi-GPU plumbing; pointers are CUDA device pointers) */
 typedef struct fdw_devinfo {

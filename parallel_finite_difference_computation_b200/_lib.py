@@ -57,6 +57,11 @@ class DevInfo(C.Structure):
                 ("li0", C.c_int), ("nli", C.c_int)]
 
 
+class PeerInfo(C.Structure):
+    _fields_ = [("field", (C.c_ubyte * 64) * 4), ("flags", C.c_ubyte * 64), ("pitch", C.c_longlong),
+                ("nloc", C.c_int), ("gx0", C.c_int), ("device", C.c_int), ("reserved", C.c_int)]
+
+
 # every symbol include/fdwave.h declares: (restype, argtypes)
 _optf32 = C.c_void_p  # optional float* (may be NULL)
 SIGNATURES = {
@@ -97,6 +102,12 @@ SIGNATURES = {
     "fdw_set_v2_local": (C.c_int, [C.c_void_p, f32p]),
     "fdw_fields_upload_local": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p]),
     "fdw_fields_download_local": (C.c_int, [C.c_void_p, C.c_int, _optf32, _optf32]),
+    "fdw_peer_export": (C.c_int, [C.c_void_p, C.POINTER(PeerInfo)]),
+    "fdw_peer_attach": (C.c_int, [C.c_void_p, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]),
+    "fdw_peer_detach": (C.c_int, [C.c_void_p]),
+    "fdw_peer_refresh": (C.c_int, [C.c_void_p]),
+    "fdw_peer_levels": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "fdw_peer_fence": (C.c_int, [C.c_void_p]),
     "fdw_devinfo_get": (C.c_int, [C.c_void_p, C.POINTER(DevInfo)]),
     "fdw_mark_begin": (C.c_int, [C.c_void_p]),
     "fdw_mark_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

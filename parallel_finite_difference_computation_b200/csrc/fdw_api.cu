@@ -103,6 +103,16 @@ struct fdw_ctx {
     int li0 = 0, nli = 0; /* interior x rows owned by this slab: global rows [li0, li0+nli) */
     /* split-phase shot state (slab decomposition) */
     int phase = 0, shot_gz = 0, shot_is = 0, shot_ns = 1;
+    /* peer-memory halo exchange (slab decomposition over NVLink P2P) */
+    struct PeerSide {
+        bool on = false;
+        float *fbase[4] = {nullptr, nullptr, nullptr, nullptr}; /* the neighbour's four field allocations, mapped here */
+        unsigned *flags = nullptr;                              /* the neighbour's flag block, mapped here */
+        int nloc = 0;
+    } peer[2];                 /* [0] lower neighbour (rows below gx0), [1] upper neighbour */
+    unsigned *flags_d = nullptr; /* written by the neighbours: [0] by the lower one, [1] by the upper one */
+    unsigned peer_seq = 0;       /* boundary-row pushes issued so far (lock-step on all slabs) */
+    long long peer_waits = 0;
     /* split-phase step (slab decomposition) */
     bool step_open = false;
     StepArgs step_args;
@@ -137,7 +147,47 @@ __global__ void k_materialize(float *r0, long long pitch, int nze, int row_lo, i
     r0[(long long)lr * pitch + j] = v;
 }
 
+/* peer-memory halo exchange: release / acquire of the "boundary rows delivered" counters.  The
+ * signal kernel runs after the boundary-strip launch in stream order (its peer stores are
+ * complete at the kernel boundary); the system-scope fence orders them before the flag. */
+__global__ void k_peer_signal(unsigned *flag_lo, unsigned *flag_hi, unsigned v)
+{
+#ifndef FDW_EMU
+    __threadfence_system();
+#endif
+    if (flag_lo) *(volatile unsigned *)flag_lo = v;
+    if (flag_hi) *(volatile unsigned *)flag_hi = v;
+#ifndef FDW_EMU
+    __threadfence_system();
+#endif
+}
+
+__global__ void k_peer_wait(const unsigned *mine, unsigned v, int need_lo, int need_hi, int *error_flag)
+{
 #ifdef FDW_EMU
+    /* the host stand-in runs everything synchronously: an unmet flag is a protocol error */
+    if ((need_lo && mine[0] < v) || (need_hi && mine[1] < v)) *error_flag = 2;
+#else
+    const long long t0 = clock64();
+    for (int s = 0; s < 2; s++) {
+        if (!(s == 0 ? need_lo : need_hi)) continue;
+        while (*((volatile const unsigned *)mine + s) < v) {
+            if (clock64() - t0 > (1LL << 33)) { /* ~4 s: never hang the GPU on a lost neighbour */
+                atomicExch(error_flag, 2);
+                return;
+            }
+        }
+    }
+    __threadfence_system();
+#endif
+}
+
+#ifdef FDW_EMU
+static void thunk_peer_signal(void **a) { k_peer_signal(*(unsigned **)a[0], *(unsigned **)a[1], *(unsigned *)a[2]); }
+static void thunk_peer_wait(void **a)
+{
+    k_peer_wait(*(const unsigned **)a[0], *(unsigned *)a[1], *(int *)a[2], *(int *)a[3], *(int **)a[4]);
+}
 static void thunk_scale_rows(void **a) { k_scale_rows(*(float **)a[0], *(long long *)a[1], *(float *)a[2]); }
 static void thunk_materialize(void **a)
 {
@@ -451,10 +501,11 @@ static int run_levels(fdw_ctx *c, int recipe, int epi, bool sponge, bool source,
 
 static int check_device_flag(fdw_ctx *c)
 {
-    if (c->persist_launches == 0) return FDW_OK;
+    if (c->persist_launches == 0 && c->peer_waits == 0) return FDW_OK;
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, c->errflag_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (flag == 2) { fdw_set_error("peer halo exchange: a neighbour's boundary rows never arrived"); return FDW_ERR_CUDA; }
     if (flag) { fdw_set_error("persistent kernel: grid barrier timed out"); return FDW_ERR_CUDA; }
     return FDW_OK;
 }
@@ -681,6 +732,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
         TRY(cudaMalloc(&c->hist, (size_t)prm->nt * img_elems * sizeof(float)));
     }
     TRY(cudaMalloc(&c->barrier_d, sizeof(unsigned)));
+    TRY(cudaMalloc(&c->flags_d, 2 * sizeof(unsigned)));
+    TRY(cudaMemsetAsync(c->flags_d, 0, 2 * sizeof(unsigned), c->stream));
     TRY(cudaMalloc(&c->errflag_d, sizeof(int)));
     TRY(cudaMemsetAsync(c->errflag_d, 0, sizeof(int), c->stream));
     TRY(cudaStreamSynchronize(c->stream)); /* the staging vectors go out of scope */
@@ -694,6 +747,8 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     if (!c) return;
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    fdw_peer_detach(c);
+    cudaFree(c->flags_d);
     for (int k = 0; k < 4; k++) cudaFree(c->f[k].base);
     cudaFree(c->vdt_base); cudaFree(c->tz_base); cudaFree(c->tx_base);
     cudaFree(c->hist); cudaFree(c->img); cudaFree(c->dobs_d); cudaFree(c->rec_d);
@@ -1175,6 +1230,174 @@ extern "C" int fdw_fields_download_local(fdw_ctx *c, int pair, float *newest, fl
     if (older) { CHECK(materialize(c, o)); CHECK(rows_d2h(c, o.r0, older)); }
     CU(cudaStreamSynchronize(c->stream));
     return FDW_OK;
+}
+
+/* ------------------------------------------------------------------ peer-memory halo exchange
+ * One process per GPU: every slab exports CUDA IPC handles of its field buffers and flag block,
+ * the neighbours map them, and from then on a time level needs no host-side communication call:
+ * the boundary-strip launch stores its rows locally AND straight into the neighbour's ghost rows
+ * over NVLink (EPI_PUSH), a release flag follows it in stream order, the interior launch overlaps
+ * the transfer, and the next level's boundary launch is gated by an acquire wait on the flags the
+ * neighbours wrote here.  Safety of the unsynchronised ghost-row writes: a slab writes level n+1
+ * into the neighbour's copy of buffer Y only after it has seen the neighbour's flag n, which the
+ * neighbour raises after its own last reader of Y's ghost rows (its boundary launch of level n)
+ * has completed; fdw_peer_fence closes a run so that no push is still in flight when the caller
+ * goes on to zero, upload or download the buffers. */
+static_assert(sizeof(cudaIpcMemHandle_t) <= FDW_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int fdw_peer_export(fdw_ctx *c, fdw_peer_info *out)
+{
+    if (!c || !out) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    for (int k = 0; k < 4; k++) {
+        CU(cudaIpcGetMemHandle(&h, c->f[k].base));
+        memcpy(out->field[k], &h, sizeof h);
+    }
+    CU(cudaIpcGetMemHandle(&h, c->flags_d));
+    memcpy(out->flags, &h, sizeof h);
+    out->nloc = c->nloc; out->gx0 = c->gx0; out->device = c->prm.device; out->pitch = c->pitch;
+    return FDW_OK;
+}
+
+extern "C" int fdw_peer_detach(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    for (int s = 0; s < 2; s++) {
+        fdw_ctx::PeerSide &p = c->peer[s];
+        if (!p.on) continue;
+        for (int k = 0; k < 4; k++)
+            if (p.fbase[k]) cudaIpcCloseMemHandle(p.fbase[k]);
+        if (p.flags) cudaIpcCloseMemHandle(p.flags);
+        p = fdw_ctx::PeerSide();
+    }
+    return FDW_OK;
+}
+
+extern "C" int fdw_peer_attach(fdw_ctx *c, const fdw_peer_info *lo, const fdw_peer_info *hi)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CU(cudaStreamSynchronize(c->stream));
+    fdw_peer_detach(c);
+    const fdw_peer_info *info[2] = {lo, hi};
+    for (int s = 0; s < 2; s++) {
+        if (!info[s]) continue;
+        const fdw_peer_info &pi = *info[s];
+        const bool adjacent = s == 0 ? pi.gx0 + pi.nloc == c->gx0 : c->gx0 + c->nloc == pi.gx0;
+        if (pi.pitch != c->pitch || !adjacent || pi.nloc < 2 * GUARD || c->nloc < 2 * GUARD) {
+            fdw_set_error("fdw_peer_attach: neighbour %d (rows %d+%d, pitch %lld) does not adjoin this slab (rows %d+%d, pitch %lld)",
+                          s, pi.gx0, pi.nloc, pi.pitch, c->gx0, c->nloc, c->pitch);
+            fdw_peer_detach(c);
+            return FDW_ERR_ARG;
+        }
+        fdw_ctx::PeerSide &p = c->peer[s];
+        cudaIpcMemHandle_t h;
+        for (int k = 0; k < 4; k++) {
+            memcpy(&h, pi.field[k], sizeof h);
+            CU(cudaIpcOpenMemHandle((void **)&p.fbase[k], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        memcpy(&h, pi.flags, sizeof h);
+        CU(cudaIpcOpenMemHandle((void **)&p.flags, h, cudaIpcMemLazyEnablePeerAccess));
+        p.nloc = pi.nloc;
+        p.on = true;
+    }
+    c->peer_seq = 0;
+    CU(cudaMemsetAsync(c->flags_d, 0, 2 * sizeof(unsigned), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FDW_OK;
+}
+
+/* peer-mapped address that corresponds to this slab's local row 0, column 0 in the neighbour's
+ * field buffer k: the lower neighbour's upper ghost rows start at its row nloc, the upper
+ * neighbour's lower ghost rows end at its row 0 */
+static float *peer_image(const fdw_ctx *c, int side, int k)
+{
+    const fdw_ctx::PeerSide &p = c->peer[side];
+    if (!p.on) return nullptr;
+    float *r0 = p.fbase[k] + (size_t)(GUARD + 1) * c->pitch;
+    return side == 0 ? r0 + (long long)p.nloc * c->pitch : r0 - (long long)c->nloc * c->pitch;
+}
+
+static int peer_wait(fdw_ctx *c)
+{
+    int need_lo = c->peer[0].on, need_hi = c->peer[1].on;
+    if (!need_lo && !need_hi) return FDW_OK;
+    const unsigned *mine = c->flags_d;
+    unsigned v = c->peer_seq;
+    void *params[] = {&mine, &v, &need_lo, &need_hi, &c->errflag_d};
+    CU(cudaLaunchKernel(FDW_KPTR(k_peer_wait, thunk_peer_wait), dim3(1), dim3(1), params, 0, c->stream));
+    c->launches++;
+    c->peer_waits++;
+    return FDW_OK;
+}
+
+static int peer_signal(fdw_ctx *c)
+{
+    c->peer_seq++;
+    /* this slab is the lower neighbour's upper neighbour (slot 1 there) and vice versa */
+    unsigned *flo = c->peer[0].on ? c->peer[0].flags + 1 : nullptr;
+    unsigned *fhi = c->peer[1].on ? c->peer[1].flags + 0 : nullptr;
+    unsigned v = c->peer_seq;
+    void *params[] = {&flo, &fhi, &v};
+    CU(cudaLaunchKernel(FDW_KPTR(k_peer_signal, thunk_peer_signal), dim3(1), dim3(1), params, 0, c->stream));
+    c->launches++;
+    return FDW_OK;
+}
+
+extern "C" int fdw_peer_levels(fdw_ctx *c, int it0, int nsteps)
+{
+    if (!c || nsteps < 0) return FDW_ERR_ARG;
+    if (!c->peer[0].on && !c->peer[1].on) { fdw_set_error("fdw_peer_levels: no neighbour attached"); return FDW_ERR_STATE; }
+    const int nc = c->ncol4;
+    for (int it = it0; it < it0 + nsteps; it++) {
+        CHECK(fdw_step_begin(c, it));
+        StepArgs a = c->step_args;
+        const int epi = phase_epi(c->phase);
+        const int wbuf = c->older[0]; /* the buffer this level is written to -- the same index on every slab */
+        a.push_lo = peer_image(c, 0, wbuf);
+        a.push_hi = peer_image(c, 1, wbuf);
+        a.push_nloc = c->nloc;
+        const int ilo = c->peer[0].on ? GUARD : 0, ihi = c->peer[1].on ? c->nloc - GUARD : c->nloc;
+        int rc = peer_wait(c); /* the neighbours' rows of the newest level have landed in the ghost rows */
+        for (int s = 0; s < 2 && rc == FDW_OK; s++) {
+            if (!c->peer[s].on) continue;
+            int r0 = s == 0 ? 0 : c->nloc - GUARD, r1 = s == 0 ? GUARD : c->nloc;
+            if (r0 < a.row0) r0 = a.row0;
+            if (r1 > a.row1) r1 = a.row1;
+            Rect strip = {0, nc, r0, r1, 1};
+            rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strip, c->stream);
+        }
+        if (rc == FDW_OK) rc = peer_signal(c);
+        if (rc == FDW_OK) rc = launch_level(c, c->step_args, c->prm.recipe, epi, ilo, ihi, c->stream);
+        if (rc != FDW_OK) { c->step_open = false; return rc; }
+        CHECK(fdw_step_end(c));
+    }
+    return FDW_OK;
+}
+
+extern "C" int fdw_peer_refresh(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    const int k = c->newest[0];
+    const size_t bytes = (size_t)GUARD * c->pitch * sizeof(float);
+    const float *r0 = c->f[k].r0;
+    if (c->peer[0].on)
+        CU(cudaMemcpyAsync(peer_image(c, 0, k), r0, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->peer[1].on)
+        CU(cudaMemcpyAsync(peer_image(c, 1, k) + (long long)(c->nloc - GUARD) * c->pitch,
+                           r0 + (long long)(c->nloc - GUARD) * c->pitch, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CHECK(peer_signal(c));
+    return FDW_OK;
+}
+
+extern "C" int fdw_peer_fence(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    return peer_wait(c);
 }
 
 /* ------------------------------------------------------------------ device-resident access */

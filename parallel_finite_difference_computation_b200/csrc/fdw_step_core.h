@@ -43,7 +43,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 v 
 namespace fdw {
 
 enum { RECIPE_G = 0, RECIPE_C = 1, RECIPE_FAST = 2 };
-enum { EPI_RECORD = 1, EPI_INJECT = 2, EPI_HSTORE = 4, EPI_IMG_HIST = 8, EPI_IMG_FIELD = 16 };
+enum { EPI_RECORD = 1, EPI_INJECT = 2, EPI_HSTORE = 4, EPI_IMG_HIST = 8, EPI_IMG_FIELD = 16, EPI_PUSH = 32 };
 enum { GUARD = 4 }; /* guard/ghost rows above and below every slab; >= order/2 */
 
 struct StepArgs {
@@ -88,6 +88,12 @@ struct StepArgs {
     float *img;
     int img_gi0, img_n;
     const float *img_field; /* EPI_IMG_FIELD: reconstructed source level, field layout */
+    /* EPI_PUSH (slab decomposition over peer memory): the first / last GUARD owned rows are also
+     * stored straight into the neighbour's ghost rows.  push_lo / push_hi are the peer-mapped
+     * addresses that correspond to THIS slab's local row 0, column 0 in the lower / upper
+     * neighbour's copy of the level being written (same pitch); null = no neighbour. */
+    float *push_lo, *push_hi;
+    int push_nloc;
 };
 
 /* the few quantities that change from one time level to the next; the ordinary kernels copy
@@ -362,6 +368,13 @@ FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int 
                         if (j0 + k == a.inj_j) res[k] = fadd(res[k], s);
                 }
                 st4(ppc, make_float4(res[0], res[1], res[2], res[3]));
+                /* ---- halo push: boundary rows go to the neighbour's ghost rows over NVLink */
+                if (EPI & EPI_PUSH) {
+                    if (a.push_lo && lr < GUARD)
+                        st4(a.push_lo + (long long)lr * pitch + j0, make_float4(res[0], res[1], res[2], res[3]));
+                    if (a.push_hi && lr >= a.push_nloc - GUARD)
+                        st4(a.push_hi + (long long)lr * pitch + j0, make_float4(res[0], res[1], res[2], res[3]));
+                }
 
                 /* ---- seismogram sample: the newer level after one more sponge pass */
                 if ((EPI & EPI_RECORD) && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n && a.rec_j >= j0 &&

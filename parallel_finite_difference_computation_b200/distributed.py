@@ -4,11 +4,19 @@ The reference has no multi-GPU code; both partitionings are
 new, and neither changes the per-point arithmetic:
 
 * slab decomposition (SlabPropagator): the extended grid is cut along x (the
-  slow axis, so a halo is GUARD contiguous rows) into `world` slabs.  Per time
-  level each rank (1) updates its two GUARD-row boundary strips, (2) starts the
-  exchange of those rows with its neighbours on a communication stream while
-  (3) the interior rows are updated on the compute stream, (4) joins.  An
-  N-slab run reproduces the single-domain result bit for bit.
+  slow axis, so a halo is GUARD contiguous rows) into `world` slabs.  Two
+  exchange mechanisms, same results bit for bit (and equal to one domain):
+    halo="p2p"  (default on GPUs) neighbouring processes map each other's field
+                buffers through CUDA IPC once; per level the boundary-strip
+                kernel stores its rows locally AND into the neighbour's ghost
+                rows over NVLink, a release flag follows, the interior update
+                overlaps the transfer, the next level's boundary launch waits
+                on the device for the neighbours' flags (fdw_peer_levels: the
+                whole level loop runs inside the C library, no per-level host
+                communication call);
+    halo="nccl" boundary strips -> batch_isend_irecv on a communication stream
+                while the interior updates -> join (also the gloo path of the
+                CPU unit tests).
 * shot parallelism (shot_partition / reduce_image): shots are independent
   units; the only collective is the final image sum.
 
@@ -50,8 +58,11 @@ class _CudaView:
 class SlabPropagator:
     """Wave2D over one slab of a slab-decomposed grid (world == 1: the whole grid)."""
 
-    def __init__(self, nx, nz, nxb, nzb, dx, dz, dt, rank=0, world=1, device=0, lib=None, on_gpu=True, **kw):
+    def __init__(self, nx, nz, nxb, nzb, dx, dz, dt, rank=0, world=1, device=0, lib=None, on_gpu=True, halo=None,
+                 **kw):
         self.rank, self.world, self.on_gpu = rank, world, on_gpu
+        self.halo = halo or ("p2p" if on_gpu else "nccl")
+        self._attached = False
         self.nxe, self.nze = nx + 2 * nxb, nz + 2 * nzb
         self.slab = slab_rows(self.nxe, world, rank)
         self.nloc = self.slab[1] - self.slab[0]
@@ -73,6 +84,34 @@ class SlabPropagator:
     def close(self):
         self.w.close()
 
+    def attach_peers(self):
+        """halo="p2p": exchange the CUDA IPC handles of the slab buffers (all_gather over the
+        process group -- plumbing, once) and map the two neighbours' buffers"""
+        if self.world == 1 or self._attached:
+            return
+        import torch.distributed as dist
+        mine = _lib.PeerInfo()
+        _lib.check(self.L, self.L.fdw_peer_export(self.h, C.byref(mine)))
+        infos = [None] * self.world
+        dist.all_gather_object(infos, bytes(mine))
+        lo = _lib.PeerInfo.from_buffer_copy(infos[self.rank - 1]) if self.rank > 0 else None
+        hi = _lib.PeerInfo.from_buffer_copy(infos[self.rank + 1]) if self.rank < self.world - 1 else None
+        _lib.check(self.L, self.L.fdw_peer_attach(self.h, C.byref(lo) if lo else None, C.byref(hi) if hi else None))
+        dist.barrier()  # nobody pushes before every slab has zeroed its flags
+        self._attached = True
+
+    def _peer_refresh(self):
+        """after this slab's buffers were zeroed or uploaded: push the newest level's boundary rows
+        and raise the flag; the neighbours' first boundary launch of the next level waits for it
+        (so it can never push into a buffer that is still to be zeroed)"""
+        self.attach_peers()
+        _lib.check(self.L, self.L.fdw_peer_refresh(self.h))
+        _lib.check(self.L, self.L.fdw_peer_fence(self.h))
+
+    @property
+    def p2p(self):
+        return self.world > 1 and self.on_gpu and self.halo == "p2p"
+
     def set_stream(self, cuda_stream):
         self.w.set_stream(cuda_stream)
         self._compute_stream = cuda_stream
@@ -85,6 +124,8 @@ class SlabPropagator:
 
     def zero(self):
         self.w.zero()
+        if self.p2p:
+            self._peer_refresh()
 
     def launch_count(self):
         return self.w.launch_count()
@@ -138,6 +179,9 @@ class SlabPropagator:
         if self.world == 1:
             return
         import torch.distributed as dist
+        if self.p2p:
+            self._peer_refresh()
+            return
         if self.on_gpu:
             self.w.sync()
         for r in dist.batch_isend_irecv(self._exchange_ops(0)):
@@ -161,6 +205,8 @@ class SlabPropagator:
             ns = dobs_all.size // (self.w.nx * self.w.nt)
             ptr = dobs_all.ctypes.data_as(C.c_void_p)
         _lib.check(L, L.fdw_shot_begin(h, phase, sx, sz, gz, ptr, ns, is_))
+        if self.p2p:
+            self._peer_refresh()  # the phase zeroed the fields
         self._levels(0, self.w.nt)
 
     def model_shot(self, sx, sz, gz):
@@ -206,6 +252,11 @@ class SlabPropagator:
                 _lib.check(L, L.fdw_step_begin(h, it))
                 _lib.check(L, L.fdw_step_rows(h, 0, self.nloc, None))
                 _lib.check(L, L.fdw_step_end(h))
+            return
+        if self.p2p:
+            self.attach_peers()
+            _lib.check(L, L.fdw_peer_levels(h, it0, nsteps))
+            _lib.check(L, L.fdw_peer_fence(h))
             return
         import torch.distributed as dist
         lo_nb, hi_nb = self.rank > 0, self.rank < self.world - 1

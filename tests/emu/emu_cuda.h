@@ -69,4 +69,11 @@ cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **arg
 cudaError_t cudaLaunchCooperativeKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t);
 enum { cudaDevAttrCooperativeLaunch = 95 };
 cudaError_t cudaDeviceGetAttribute(int *value, int attr, int device);
+/* "IPC" inside one process: the handle carries the pointer itself (two slab contexts of the
+ * same test process can then push into each other's buffers) */
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *);
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned);
+cudaError_t cudaIpcCloseMemHandle(void *);
 #endif

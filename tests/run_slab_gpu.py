@@ -3,10 +3,12 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tests/run_slab_gpu.py
 
-Every rank propagates its slab of a 4096 x 4096 grid for 40 levels with the
-NCCL halo exchange; rank 0 also runs the whole grid alone and the gathered
-slabs must equal it bit for bit (decomposition does not change the
-per-point arithmetic)."""
+Every rank propagates its slab of a 4096 x 4096 grid for 40 levels, once with
+the peer-memory halo exchange (halo="p2p": boundary rows stored into the
+neighbour's ghost rows over NVLink by the step kernel) and once with NCCL
+send/recv; rank 0 also runs the whole grid alone and the gathered slabs must
+equal it bit for bit (decomposition does not change the per-point
+arithmetic)."""
 import os
 import sys
 
@@ -18,6 +20,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import parallel_finite_difference_computation_b200 as fdw  # noqa: E402
 from parallel_finite_difference_computation_b200 import distributed as D  # noqa: E402
+
+
+HALOS = tuple(os.environ.get("FDW_HALOS", "p2p,nccl").split(","))
 
 
 def main():
@@ -36,18 +41,23 @@ def main():
     srce = fdw.host.ricker_wavelet(nt, 0.001, 25.0, fdw.FAMILY_GPU)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, rank=rank, world=world, device=lrank, order=8,
-                          fac=0.75, family=fdw.FAMILY_GPU, taper=fdw.TAPER_TOP, nt=nt)
-    sp.set_stream(stream.cuda_stream)
-    x0, x1 = sp.slab
-    sp.set_v2_local(v2[x0:x1])
-    sp.set_wavelet(srce)
-    sp.set_source(D.slab_rows(n, world, 0)[1] - 2, nb)  # the same global point on every rank, next to a slab cut
-    na, nb_ = a[x0:x1].copy(), b[x0:x1].copy()  # copies: propagate_local works in place
-    sp.propagate_local(na, nb_, 0, nt)
-    torch.cuda.synchronize()
-    parts = [None] * world
-    dist.all_gather_object(parts, (na, nb_))
+    results = {}
+    for halo in HALOS:
+        sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, rank=rank, world=world, device=lrank, order=8,
+                              fac=0.75, family=fdw.FAMILY_GPU, taper=fdw.TAPER_TOP, nt=nt, halo=halo)
+        sp.set_stream(stream.cuda_stream)
+        x0, x1 = sp.slab
+        sp.set_v2_local(v2[x0:x1])
+        sp.set_wavelet(srce)
+        sp.set_source(D.slab_rows(n, world, 0)[1] - 2, nb)  # the same global point on every rank, next to a slab cut
+        na, nb_ = a[x0:x1].copy(), b[x0:x1].copy()  # copies: propagate_local works in place
+        sp.propagate_local(na, nb_, 0, nt // 2)
+        sp.propagate_local(na, nb_, nt // 2, nt - nt // 2)  # a second upload/refresh/advance cycle
+        torch.cuda.synchronize()
+        parts = [None] * world
+        dist.all_gather_object(parts, (na, nb_))
+        results[halo] = parts
+        sp.close()
     ok = True
     if rank == 0:
         with fdw.Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, order=8, fac=0.75, family=fdw.FAMILY_GPU,
@@ -56,19 +66,22 @@ def main():
             w.set_wavelet(srce)
             w.set_source(D.slab_rows(n, world, 0)[1] - 2, nb)
             w.propagate(a, b, 0, nt)
-        newest = np.concatenate([p[0] for p in parts])
-        older = np.concatenate([p[1] for p in parts])
-        ok = np.array_equal(newest.view(np.uint32), a.view(np.uint32)) and \
-            np.array_equal(older.view(np.uint32), b.view(np.uint32))
-        print("slab x%d vs single domain bitwise: %s" % (world, "OK" if ok else "MISMATCH"), flush=True)
-    ok = check_domain_divided_cpu_family(rank, world, lrank) and ok
+        for halo, parts in results.items():
+            newest = np.concatenate([p[0] for p in parts])
+            older = np.concatenate([p[1] for p in parts])
+            good = np.array_equal(newest.view(np.uint32), a.view(np.uint32)) and \
+                np.array_equal(older.view(np.uint32), b.view(np.uint32))
+            print("slab x%d halo=%s vs single domain bitwise: %s" % (world, halo, "OK" if good else "MISMATCH"), flush=True)
+            ok = ok and good
+    for halo in HALOS:
+        ok = check_domain_divided_cpu_family(rank, world, lrank, halo) and ok
     ok = check_shot_parallel(rank, world, lrank) and ok
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
 
-def check_domain_divided_cpu_family(rank, world, lrank):
+def check_domain_divided_cpu_family(rank, world, lrank, halo):
     """config 5: mod_main + rtm_main algorithm, slab-decomposed over the GPUs (history sharded),
     vs the same shot on one GPU: seismogram and image bit for bit."""
     nx, nz, nb, nt = 1500, 700, 40, 120
@@ -81,14 +94,14 @@ def check_domain_divided_cpu_family(rank, world, lrank):
     sx, sz, gz = nb + nx // 2 - 3, nb, nb
     kw = dict(order=8, fac=0.01, family=fdw.FAMILY_CPU, nt=nt)
     sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, rank=rank, world=world, device=lrank,
-                          taper=fdw.TAPER_FOUR, **kw)
+                          taper=fdw.TAPER_FOUR, halo=halo, **kw)
     sp.set_stream(torch.cuda.current_stream().cuda_stream)
     x0, x1 = sp.slab
     sp.set_v2_local(v2[x0:x1]); sp.set_wavelet(srce)
     data = sp.gather_rows(sp.model_shot(sx, sz, gz))
     sp.close()
     sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, rank=rank, world=world, device=lrank,
-                          taper=fdw.TAPER_TOP, history=True, **kw)
+                          taper=fdw.TAPER_TOP, history=True, halo=halo, **kw)
     sp.set_stream(torch.cuda.current_stream().cuda_stream)
     sp.set_v2_local(v2[x0:x1]); sp.set_wavelet(srce)
     img = sp.gather_rows(sp.rtm_shot_cpu(sx, sz, gz, data[None], 0))
@@ -102,8 +115,8 @@ def check_domain_divided_cpu_family(rank, world, lrank):
             w.set_v2(v2); w.set_wavelet(srce)
             i1 = w.rtm_shot_cpu(sx, sz, gz, d1[None], 0)
         ok = np.array_equal(data.view(np.uint32), d1.view(np.uint32)) and np.array_equal(img.view(np.uint32), i1.view(np.uint32))
-        print("domain-divided mod_main+rtm_main x%d vs one GPU bitwise: %s (|img|max %.3g)" % (
-            world, "OK" if ok else "MISMATCH", np.abs(i1).max()), flush=True)
+        print("domain-divided mod_main+rtm_main x%d halo=%s vs one GPU bitwise: %s (|img|max %.3g)" % (
+            world, halo, "OK" if ok else "MISMATCH", np.abs(i1).max()), flush=True)
     return ok
 
 

@@ -1,0 +1,164 @@
+"""CPU-only: the peer-memory halo exchange (fdw_peer_*: boundary rows stored straight into the
+neighbour's ghost rows by the step kernel, flag release/acquire instead of a communication
+library) must reproduce the single-domain result bit for bit.
+
+Runs on the host build (tests/emu): there "CUDA IPC" hands over plain pointers, so the slab
+contexts of ONE process can map each other, and kernels execute synchronously -- the slabs are
+therefore stepped in lock-step, one level at a time, and an acquire wait that finds its flag unmet
+is reported as a protocol error instead of spinning.  The real thing (one process per GPU, NVLink)
+is checked by tests/run_slab_gpu.py on a multi-GPU box."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import parity_cases as PC
+from emu_loader import load as load_emu
+from oracle import oracle as O
+from parallel_finite_difference_computation_b200 import (FAMILY_CPU, FAMILY_GPU, SRC_GAUSS7, SRC_POINT, TAPER_FOUR,
+                                                         TAPER_TOP, FdwError, Wave2D, _lib)
+from parallel_finite_difference_computation_b200.distributed import slab_rows
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
+
+
+def _attach_all(emu, slabs):
+    infos = []
+    for w in slabs:
+        pi = _lib.PeerInfo()
+        _lib.check(emu, emu.fdw_peer_export(w.h, C.byref(pi)))
+        infos.append(pi)
+    for r, w in enumerate(slabs):
+        lo = C.byref(infos[r - 1]) if r > 0 else None
+        hi = C.byref(infos[r + 1]) if r < len(slabs) - 1 else None
+        _lib.check(emu, emu.fdw_peer_attach(w.h, lo, hi))
+
+
+def _lockstep(emu, slabs, it0, n):
+    for it in range(it0, it0 + n):
+        for w in slabs:
+            _lib.check(emu, emu.fdw_peer_levels(w.h, it, 1))
+    for w in slabs:
+        _lib.check(emu, emu.fdw_peer_fence(w.h))
+        w.sync()  # reports a failed acquire
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("family,taper", [(FAMILY_GPU, TAPER_TOP), (FAMILY_CPU, TAPER_FOUR)])
+def test_peer_push_matches_single_domain_bitwise(emu, world, family, taper):
+    rng = np.random.default_rng(7)
+    nx, nz, nxb, nzb, nt = 53, 37, 9, 8, 14
+    nxe, nze = nx + 2 * nxb, nz + 2 * nzb
+    v2 = PC.layered_v2(nx, nz, nxb, nzb, rng)
+    a = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    b = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    srce = O.ricker_wavelet(nt, 0.001, 30.0, O.FAM_G if family == FAMILY_GPU else O.FAM_C)
+    fac = 0.6 if family == FAMILY_GPU else 0.11
+    kw = dict(order=8, fac=fac, family=family, taper=taper, nt=nt, lib=emu)
+    # single domain
+    with Wave2D(nx, nz, nxb, nzb, 10.0, 12.5, 0.001, **kw) as w:
+        w.set_v2(v2)
+        w.set_wavelet(srce)
+        w.set_source(nxb + nx // 2, nzb + 1, SRC_POINT)
+        ra, rb = a.copy(), b.copy()
+        w.propagate(ra, rb, 0, nt)
+    # slabs, peer exchange
+    slabs = [Wave2D(nx, nz, nxb, nzb, 10.0, 12.5, 0.001, slab=slab_rows(nxe, world, r), **kw) for r in range(world)]
+    try:
+        _attach_all(emu, slabs)
+        for r, w in enumerate(slabs):
+            x0, x1 = slab_rows(nxe, world, r)
+            _lib.check(emu, emu.fdw_set_v2_local(w.h, np.ascontiguousarray(v2[x0:x1])))
+            w.set_wavelet(srce)
+            w.set_source(nxb + nx // 2, nzb + 1, SRC_POINT)
+            _lib.check(emu, emu.fdw_fields_upload_local(w.h, 0, np.ascontiguousarray(a[x0:x1]),
+                                                        np.ascontiguousarray(b[x0:x1])))
+        for w in slabs:
+            _lib.check(emu, emu.fdw_peer_refresh(w.h))
+        _lockstep(emu, slabs, 0, nt)
+        for r, w in enumerate(slabs):
+            x0, x1 = slab_rows(nxe, world, r)
+            n = np.zeros((x1 - x0, nze), np.float32)
+            o = np.zeros((x1 - x0, nze), np.float32)
+            _lib.check(emu, emu.fdw_fields_download_local(w.h, 0, n.ctypes.data_as(C.c_void_p),
+                                                          o.ctypes.data_as(C.c_void_p)))
+            PC.assert_bit_equal(n, ra[x0:x1], "newest, slab %d/%d" % (r, world))
+            PC.assert_bit_equal(o, rb[x0:x1], "older, slab %d/%d" % (r, world))
+    finally:
+        for w in slabs:
+            w.close()
+
+
+def test_peer_modelling_shot_records_like_single_domain(emu):
+    """mod_main shot (7x7 source, four-sided sponge, seismogram epilogue) through the peer path"""
+    rng = np.random.default_rng(11)
+    nx, nz, nxb, nzb, nt, world = 41, 29, 8, 8, 12, 2
+    nxe = nx + 2 * nxb
+    v2 = PC.layered_v2(nx, nz, nxb, nzb, rng)
+    srce = O.ricker_wavelet(nt, 0.001, 30.0, O.FAM_C)
+    kw = dict(order=8, fac=0.11, family=FAMILY_CPU, recipe=_lib.RECIPE_C, taper=TAPER_FOUR, nt=nt, lib=emu)
+    sx, sz, gz = nxb + nx // 2, nzb + 2, nzb + 1
+    with Wave2D(nx, nz, nxb, nzb, 10.0, 10.0, 0.001, **kw) as w:
+        w.set_v2(v2)
+        w.set_wavelet(srce)
+        want = w.model_shot(sx, sz, gz)
+    slabs = [Wave2D(nx, nz, nxb, nzb, 10.0, 10.0, 0.001, slab=slab_rows(nxe, world, r), **kw) for r in range(world)]
+    try:
+        _attach_all(emu, slabs)
+        for r, w in enumerate(slabs):
+            x0, x1 = slab_rows(nxe, world, r)
+            _lib.check(emu, emu.fdw_set_v2_local(w.h, np.ascontiguousarray(v2[x0:x1])))
+            w.set_wavelet(srce)
+            _lib.check(emu, emu.fdw_shot_begin(w.h, _lib.PHASE_MODEL, sx, sz, gz, None, 1, 0))
+        for w in slabs:
+            _lib.check(emu, emu.fdw_peer_refresh(w.h))
+        _lockstep(emu, slabs, 0, nt)
+        rows = []
+        for w in slabs:
+            d = w.devinfo()
+            out = np.zeros((max(d.nli, 1), nt), np.float32)
+            _lib.check(emu, emu.fdw_shot_end(w.h, out))
+            rows.append(out[: d.nli])
+        PC.assert_bit_equal(np.concatenate(rows), want, "seismograms")
+    finally:
+        for w in slabs:
+            w.close()
+
+
+def test_peer_protocol_errors(emu):
+    nx, nz, nb = 24, 16, 4
+    nxe = nx + 2 * nb
+    kw = dict(order=8, fac=0.5, family=FAMILY_GPU, taper=TAPER_TOP, nt=4, lib=emu)
+    a = Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, slab=(0, 16), **kw)
+    b = Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, slab=(16, nxe), **kw)
+    c = Wave2D(nx, nz + 32, nb, nb, 10.0, 10.0, 0.001, slab=(16, nxe), **kw)  # different pitch
+    try:
+        with pytest.raises(FdwError) as e:  # stepping without neighbours
+            _lib.check(emu, emu.fdw_peer_levels(a.h, 0, 1))
+        assert e.value.code == -5
+        ia, ib, ic = _lib.PeerInfo(), _lib.PeerInfo(), _lib.PeerInfo()
+        for w, i in ((a, ia), (b, ib), (c, ic)):
+            _lib.check(emu, emu.fdw_peer_export(w.h, C.byref(i)))
+        with pytest.raises(FdwError) as e:  # wrong side: b is above a, not below
+            _lib.check(emu, emu.fdw_peer_attach(a.h, C.byref(ib), None))
+        assert e.value.code == -1 and "adjoin" in str(e.value)
+        with pytest.raises(FdwError):  # pitch mismatch
+            _lib.check(emu, emu.fdw_peer_attach(a.h, None, C.byref(ic)))
+        _lib.check(emu, emu.fdw_peer_attach(a.h, None, C.byref(ib)))
+        _lib.check(emu, emu.fdw_peer_attach(b.h, C.byref(ia), None))
+        for w in (a, b):
+            w.set_v2(np.full((nxe, nz + 2 * nb), 4e6, np.float32))
+            w.set_wavelet(np.ones(4, np.float32))
+            w.set_source(nb + 3, nb + 3, SRC_POINT)
+        # a runs two levels while b has not moved: the second acquire finds b's flag unmet
+        _lib.check(emu, emu.fdw_peer_levels(a.h, 0, 1))
+        _lib.check(emu, emu.fdw_peer_levels(a.h, 1, 1))
+        with pytest.raises(FdwError) as e:
+            a.sync()
+        assert "never arrived" in str(e.value)
+    finally:
+        for w in (a, b, c):
+            w.close()
