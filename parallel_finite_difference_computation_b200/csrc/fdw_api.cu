@@ -87,7 +87,7 @@ struct fdw_ctx {
     size_t dobs_cap = 0, rec_cap = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_pfork = nullptr, ev_pjoin = nullptr;
     cudaStream_t side = nullptr;
     long long launches = 0;
     int nsm = 0;
@@ -708,6 +708,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     TRY(cudaEventCreate(&c->ev1));
     TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&c->ev_pfork, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&c->ev_pjoin, cudaEventDisableTiming));
     for (int k = 0; k < 4; k++) {
         rc = field_alloc(c, &c->f[k]);
         if (rc != FDW_OK) { fdw_destroy(c); return rc; }
@@ -757,6 +759,8 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_pfork) cudaEventDestroy(c->ev_pfork);
+    if (c->ev_pjoin) cudaEventDestroy(c->ev_pjoin);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1320,20 +1324,20 @@ static float *peer_image(const fdw_ctx *c, int side, int k)
     return side == 0 ? r0 + (long long)p.nloc * c->pitch : r0 - (long long)c->nloc * c->pitch;
 }
 
-static int peer_wait(fdw_ctx *c)
+static int peer_wait(fdw_ctx *c, cudaStream_t st)
 {
     int need_lo = c->peer[0].on, need_hi = c->peer[1].on;
     if (!need_lo && !need_hi) return FDW_OK;
     const unsigned *mine = c->flags_d;
     unsigned v = c->peer_seq;
     void *params[] = {&mine, &v, &need_lo, &need_hi, &c->errflag_d};
-    CU(cudaLaunchKernel(FDW_KPTR(k_peer_wait, thunk_peer_wait), dim3(1), dim3(1), params, 0, c->stream));
+    CU(cudaLaunchKernel(FDW_KPTR(k_peer_wait, thunk_peer_wait), dim3(1), dim3(1), params, 0, st));
     c->launches++;
     c->peer_waits++;
     return FDW_OK;
 }
 
-static int peer_signal(fdw_ctx *c)
+static int peer_signal(fdw_ctx *c, cudaStream_t st)
 {
     c->peer_seq++;
     /* this slab is the lower neighbour's upper neighbour (slot 1 there) and vice versa */
@@ -1341,7 +1345,7 @@ static int peer_signal(fdw_ctx *c)
     unsigned *fhi = c->peer[1].on ? c->peer[1].flags + 0 : nullptr;
     unsigned v = c->peer_seq;
     void *params[] = {&flo, &fhi, &v};
-    CU(cudaLaunchKernel(FDW_KPTR(k_peer_signal, thunk_peer_signal), dim3(1), dim3(1), params, 0, c->stream));
+    CU(cudaLaunchKernel(FDW_KPTR(k_peer_signal, thunk_peer_signal), dim3(1), dim3(1), params, 0, st));
     c->launches++;
     return FDW_OK;
 }
@@ -1360,17 +1364,25 @@ extern "C" int fdw_peer_levels(fdw_ctx *c, int it0, int nsteps)
         a.push_hi = peer_image(c, 1, wbuf);
         a.push_nloc = c->nloc;
         const int ilo = c->peer[0].on ? GUARD : 0, ihi = c->peer[1].on ? c->nloc - GUARD : c->nloc;
-        int rc = peer_wait(c); /* the neighbours' rows of the newest level have landed in the ghost rows */
+        /* the boundary chain (acquire -> boundary strips with the push -> release) runs on the side
+         * stream, concurrently with the interior launch: a few microseconds of small kernels and the
+         * NVLink transfer hide behind the interior update.  Both join before the next level. */
+        int rc = FDW_OK;
+        if (cudaEventRecord(c->ev_pfork, c->stream) != cudaSuccess || cudaStreamWaitEvent(c->side, c->ev_pfork, 0) != cudaSuccess)
+            rc = FDW_ERR_CUDA;
+        if (rc == FDW_OK) rc = peer_wait(c, c->side); /* the neighbours' rows of the newest level have landed */
         for (int s = 0; s < 2 && rc == FDW_OK; s++) {
             if (!c->peer[s].on) continue;
             int r0 = s == 0 ? 0 : c->nloc - GUARD, r1 = s == 0 ? GUARD : c->nloc;
             if (r0 < a.row0) r0 = a.row0;
             if (r1 > a.row1) r1 = a.row1;
             Rect strip = {0, nc, r0, r1, 1};
-            rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strip, c->stream);
+            rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strip, c->side);
         }
-        if (rc == FDW_OK) rc = peer_signal(c);
+        if (rc == FDW_OK) rc = peer_signal(c, c->side);
+        if (rc == FDW_OK && cudaEventRecord(c->ev_pjoin, c->side) != cudaSuccess) rc = FDW_ERR_CUDA;
         if (rc == FDW_OK) rc = launch_level(c, c->step_args, c->prm.recipe, epi, ilo, ihi, c->stream);
+        if (rc == FDW_OK && cudaStreamWaitEvent(c->stream, c->ev_pjoin, 0) != cudaSuccess) rc = FDW_ERR_CUDA;
         if (rc != FDW_OK) { c->step_open = false; return rc; }
         CHECK(fdw_step_end(c));
     }
@@ -1389,7 +1401,7 @@ extern "C" int fdw_peer_refresh(fdw_ctx *c)
     if (c->peer[1].on)
         CU(cudaMemcpyAsync(peer_image(c, 1, k) + (long long)(c->nloc - GUARD) * c->pitch,
                            r0 + (long long)(c->nloc - GUARD) * c->pitch, bytes, cudaMemcpyDeviceToDevice, c->stream));
-    CHECK(peer_signal(c));
+    CHECK(peer_signal(c, c->stream));
     return FDW_OK;
 }
 
@@ -1397,7 +1409,7 @@ extern "C" int fdw_peer_fence(fdw_ctx *c)
 {
     if (!c) return FDW_ERR_ARG;
     CHECK(bind(c));
-    return peer_wait(c);
+    return peer_wait(c, c->stream);
 }
 
 /* ------------------------------------------------------------------ device-resident access */
