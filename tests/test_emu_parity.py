@@ -65,6 +65,13 @@ def test_advance_wide_grid_many_chunks(emu, launch_mode):
     PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=90, nz=1100, nxb=10, nzb=12, nt=6)
 
 
+@pytest.mark.parametrize("taper", [TAPER_TOP, TAPER_NONE])
+def test_advance_ragged_bulk_tail(emu, launch_mode, taper):
+    """more than one 256-thread CTA column plus a short remainder: the ragged tail of the bulk
+    rectangle is launched as its own narrow rectangle (side stream when forking)"""
+    PC.case_advance(emu, FAMILY_GPU, RECIPE_G, taper, nx=40, nz=1300, nxb=10, nzb=12, nt=5)
+
+
 def test_fast_recipe_within_tolerance(emu):
     PC.case_advance(emu, FAMILY_GPU, RECIPE_FAST, TAPER_TOP, nt=60, tol=5e-5)
 

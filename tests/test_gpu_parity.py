@@ -75,6 +75,13 @@ def test_advance_medium_grid_many_ctas(lib):
                     src_kind=SRC_GAUSS7)
 
 
+@pytest.mark.parametrize("taper", [TAPER_TOP, TAPER_NONE])
+def test_advance_ragged_bulk_tail(lib, launch_mode, taper):
+    # > one 256-thread CTA column plus a short remainder: the bulk's ragged tail becomes its own rectangle
+    PC.case_advance(lib, FAMILY_GPU, RECIPE_G, taper, nx=40, nz=1300, nxb=10, nzb=12, nt=5)
+    PC.case_advance(lib, FAMILY_GPU, RECIPE_G, taper, nx=1200, nz=4136, nxb=20, nzb=20, nt=4)  # the C4 width
+
+
 def test_fast_recipe_within_tolerance(lib):
     # FAST = symmetric pairs + FMA + float update; tolerance from SURVEY 8d: rel-L2 <= 5e-5
     PC.case_advance(lib, FAMILY_GPU, RECIPE_FAST, TAPER_TOP, nt=200, nx=120, nz=100, nxb=20, nzb=20, tol=5e-5)
