@@ -60,6 +60,33 @@ def layered_v2(nxe, nze):
     return ve * ve
 
 
+def bind_to_gpu_numa_node(index):
+    """pin this process to the CPU cores of the GPU's NUMA node before any pinned host buffer is
+    allocated (first-touch puts the pages on that node), so that the end-to-end leg's PCIe copies of N
+    ranks do not cross the socket interconnect.  Best effort: silently does nothing off Linux/NVML."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """samples SM clock + throttle reasons of one GPU through NVML while the timed region runs"""
 
@@ -203,6 +230,7 @@ def run_ours(args):
             raise SystemExit("bench.py --gpus %d must be launched with torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    numa_node = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
@@ -314,7 +342,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * field_bytes * world,
-                "d2h_bytes_per_step": 2 * field_bytes * world, "steps": e2e_steps,
+                "d2h_bytes_per_step": 2 * field_bytes * world, "steps": e2e_steps, "host_numa_node_rank0": numa_node,
                 "note": "fdw_propagate per step: both time levels H2D from pinned host memory, %d levels, both levels D2H" % LEVELS},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -127,6 +127,51 @@ def c5_cpu_family(device):
     return out
 
 
+def c5_domain_divided(device, rank, world):
+    """BASELINE configs[4]: mod_main + rtm_main on a large synthetic model, domain-divided (slab
+    decomposition along x, forward history sharded with the slabs, halo exchange FDW_BENCH_HALO)"""
+    import torch
+    import torch.distributed as dist
+    nx, nz, nb = int(os.environ.get("FDW_C5_NX", "8192")), int(os.environ.get("FDW_C5_NZ", "2048")), 40
+    nt = int(os.environ.get("FDW_C5_NT", "300"))
+    halo = os.environ.get("FDW_BENCH_HALO", "p2p")
+    nxe, nze = nx + 2 * nb, nz + 2 * nb
+    srce = fdw.host.ricker_wavelet(nt, 0.001, 15.0, fdw.FAMILY_CPU)
+    sx, sz, gz = nb + nx // 2, nb, nb
+    kw = dict(order=8, fac=0.01, family=fdw.FAMILY_CPU, nt=nt, rank=rank, world=world, device=device, halo=halo)
+    out = {"config": "C5 mod_main + rtm_main algorithm (recipe C bit-exact), %dx%d model (+40 border), %d steps, "
+                     "domain-divided over %d GPU(s), halo=%s" % (nx, nz, nt, world, halo)}
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+
+    def timed(fn):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize(); dist.barrier()
+        return r, time.perf_counter() - t0
+
+    sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, taper=fdw.TAPER_FOUR, **kw)
+    sp.set_stream(stream.cuda_stream)
+    x0, x1 = sp.slab
+    v2 = layered(x1 - x0, nze)
+    sp.set_v2_local(v2); sp.set_wavelet(srce)
+    sp.model_shot(sx, sz, gz)
+    rows, dt = timed(lambda: sp.model_shot(sx, sz, gz))
+    out["mod_main_gpts_per_s"] = nt * nxe * nze / dt / 1e9
+    data = sp.gather_rows(rows)
+    sp.close()
+    sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, taper=fdw.TAPER_TOP, history=True, **kw)
+    sp.set_stream(stream.cuda_stream)
+    sp.set_v2_local(v2); sp.set_wavelet(srce)
+    sp.rtm_shot_cpu(sx, sz, gz, data[None], 0)
+    _, dt = timed(lambda: sp.rtm_shot_cpu(sx, sz, gz, data[None], 0))
+    out["rtm_main_gpts_per_s"] = 2 * nt * nxe * nze / dt / 1e9
+    out["history_GB_per_gpu"] = nt * max(sp.owned_interior()[1], 0) * ((nze + 4 + 31) // 32 * 32) * 4 / 1e9
+    sp.close()
+    return out
+
+
 def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -140,7 +185,10 @@ def main():
     if world == 1:
         res.append(c1_laplacian(device))
         res.append(c5_cpu_family(device))
-    res.append(c4_rtm_shots(device, rank, world))
+    if world > 1 and os.environ.get("FDW_CONFIGS", "c4,c5") .find("c5") >= 0:
+        res.append(c5_domain_divided(device, rank, world))
+    if os.environ.get("FDW_CONFIGS", "c4,c5").find("c4") >= 0:
+        res.append(c4_rtm_shots(device, rank, world))
     if rank == 0:
         for r in res:
             print(json.dumps(r))
