@@ -200,6 +200,9 @@ int fdw_halo_get(fdw_ctx *ctx, int level, fdw_halo *out);
 int fdw_set_v2_local(fdw_ctx *ctx, const float *v2_rows);
 int fdw_fields_upload_local(fdw_ctx *ctx, int pair, const float *newest, const float *older);
 int fdw_fields_download_local(fdw_ctx *ctx, int pair, float *newest, float *older);
+/* the same without the final synchronisation (pinned host arrays; fdw_sync before reading them):
+ * lets a caller keep two contexts in flight so that one job's transfers overlap the other's levels */
+int fdw_fields_download_local_async(fdw_ctx *ctx, int pair, float *newest, float *older);
 
 /* ---------------------------------------------------------------- peer-memory halo exchange
  * (one process per GPU, NVLink / NVSwitch P2P; the reference has no multi-GPU path)

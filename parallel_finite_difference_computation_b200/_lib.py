@@ -102,6 +102,7 @@ SIGNATURES = {
     "fdw_set_v2_local": (C.c_int, [C.c_void_p, f32p]),
     "fdw_fields_upload_local": (C.c_int, [C.c_void_p, C.c_int, f32p, f32p]),
     "fdw_fields_download_local": (C.c_int, [C.c_void_p, C.c_int, _optf32, _optf32]),
+    "fdw_fields_download_local_async": (C.c_int, [C.c_void_p, C.c_int, _optf32, _optf32]),
     "fdw_peer_export": (C.c_int, [C.c_void_p, C.POINTER(PeerInfo)]),
     "fdw_peer_attach": (C.c_int, [C.c_void_p, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]),
     "fdw_peer_detach": (C.c_int, [C.c_void_p]),

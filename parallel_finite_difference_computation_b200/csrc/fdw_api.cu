@@ -1256,6 +1256,16 @@ extern "C" int fdw_fields_download_local(fdw_ctx *c, int pair, float *newest, fl
     return FDW_OK;
 }
 
+extern "C" int fdw_fields_download_local_async(fdw_ctx *c, int pair, float *newest, float *older)
+{
+    if (!c || pair < 0 || pair > 1) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    Field &n = c->f[c->newest[pair]], &o = c->f[c->older[pair]];
+    if (newest) { CHECK(materialize(c, n)); CHECK(rows_d2h(c, n.r0, newest)); }
+    if (older) { CHECK(materialize(c, o)); CHECK(rows_d2h(c, o.r0, older)); }
+    return FDW_OK; /* no synchronisation: fdw_sync() before reading the host arrays */
+}
+
 /* ------------------------------------------------------------------ peer-memory halo exchange
  * One process per GPU: every slab exports CUDA IPC handles of its field buffers and flag block,
  * the neighbours map them, and from then on a time level needs no host-side communication call:

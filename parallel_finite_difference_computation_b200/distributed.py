@@ -303,6 +303,24 @@ class SlabPropagator:
         self.download_local(newest, older)
 
 
+    def propagate_local_async(self, newest, older, it0, nsteps):
+        """propagate_local without the final synchronisation: everything (uploads from the -- pinned --
+        host rows, halo refresh, nsteps levels, downloads into the same rows) is enqueued on this
+        propagator's stream; call sync() before reading the arrays.  Two propagators on two streams
+        pipeline independent jobs: one's PCIe transfers overlap the other's levels."""
+        if self.world > 1 and not self.p2p:
+            raise NotImplementedError("propagate_local_async needs the peer-memory halo exchange (halo='p2p')")
+        _lib.check(self.L, self.L.fdw_fields_upload_local(self.h, 0, newest, older))
+        if self.world > 1:
+            self._peer_refresh()
+        self.advance(it0, nsteps)
+        _lib.check(self.L, self.L.fdw_fields_download_local_async(
+            self.h, 0, newest.ctypes.data_as(C.c_void_p), older.ctypes.data_as(C.c_void_p)))
+
+    def sync(self):
+        self.w.sync()
+
+
 def reduce_image(img, op="ordered"):
     """stack per-rank partial images (img += imloc of fd-code.cu:525 / rtm_main.cpp:237).
     'ordered' gathers to every rank and sums in rank order (bit-reproducible);
