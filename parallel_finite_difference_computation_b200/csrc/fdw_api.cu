@@ -1327,15 +1327,24 @@ extern "C" int fdw_peer_attach(fdw_ctx *c, const fdw_peer_info *lo, const fdw_pe
             return FDW_ERR_ARG;
         }
         fdw_ctx::PeerSide &p = c->peer[s];
-        cudaIpcMemHandle_t h;
-        for (int k = 0; k < 4; k++) {
-            memcpy(&h, pi.field[k], sizeof h);
-            CU(cudaIpcOpenMemHandle((void **)&p.fbase[k], h, cudaIpcMemLazyEnablePeerAccess));
-        }
-        memcpy(&h, pi.flags, sizeof h);
-        CU(cudaIpcOpenMemHandle((void **)&p.flags, h, cudaIpcMemLazyEnablePeerAccess));
+        p.on = true; /* from here on fdw_peer_detach closes whatever has been mapped */
         p.nloc = pi.nloc;
-        p.on = true;
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 4 && e == cudaSuccess; k++) {
+            memcpy(&h, pi.field[k], sizeof h);
+            e = cudaIpcOpenMemHandle((void **)&p.fbase[k], h, cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e == cudaSuccess) {
+            memcpy(&h, pi.flags, sizeof h);
+            e = cudaIpcOpenMemHandle((void **)&p.flags, h, cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e != cudaSuccess) {
+            fdw_set_error("fdw_peer_attach: cudaIpcOpenMemHandle (neighbour %d, device %d): %s -- the slabs must live in "
+                          "different processes on P2P-capable GPUs", s, pi.device, cudaGetErrorString(e));
+            fdw_peer_detach(c);
+            return FDW_ERR_CUDA;
+        }
     }
     c->peer_seq = 0;
     CU(cudaMemsetAsync(c->flags_d, 0, 2 * sizeof(unsigned), c->stream));
