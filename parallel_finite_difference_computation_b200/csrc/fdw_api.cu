@@ -235,10 +235,13 @@ static const void *lap_kernel(int order)
 
 static long long pitch_for(int nze) { return ((long long)nze + 4 + 31) / 32 * 32; }
 
-/* launch geometry: one thread per float4 column, CTAs of up to 256 threads
- * tiling z; x is cut into chunks of rows_per_cta rows.  Measured on B200
- * (tools/kbench.cu): short chunks (16-32 rows) win -- the 8 halo rows a chunk
- * re-reads hit L2, while many small CTAs remove the wave-quantisation tail. */
+/* launch geometry: one thread per float4 column; CTAs tile z, x is cut into chunks of rows_per_cta
+ * rows.  Measured on B200, interleaved in one process (tools/sweep_geometry.py, profiles/
+ * r01_sweep_geometry.log): SMALL work units win -- 64-thread CTAs x 7 rows: 353 Gpts/s, 128 x 8: 339,
+ * 256 x 32: 317 on the same GPU.  The 8 halo rows a chunk re-reads are L1/L2 hits, and with ~150 k short
+ * CTAs per level neighbouring chunks run close together in time, so the L2 hit rate of those rows rises
+ * (ncu: 41 % vs 33 %) and DRAM traffic falls from 1.05x to 0.99x of the algorithmic 16 B/point. */
+enum { FDW_CTA_THREADS = 64, FDW_CTA_ROWS = 7 };
 static int cached_occupancy(const void *kern, int nthreads)
 {
     /* the occupancy query costs microseconds per call: remember it per (kernel, block size) */
@@ -255,17 +258,17 @@ static int cached_occupancy(const void *kern, int nthreads)
 static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int thr_override, int rpc_override,
                             dim3 *grid, dim3 *block, int *rows_per_cta)
 {
-    int nthreads = ncols >= 256 ? 256 : ((ncols + 31) / 32) * 32;
+    int nthreads = ncols >= FDW_CTA_THREADS ? FDW_CTA_THREADS : ((ncols + 31) / 32) * 32;
     if (thr_override > 0) nthreads = thr_override;
     if (nthreads < 32) nthreads = 32;
     int gx = (ncols + nthreads - 1) / nthreads;
-    int rpc = 32;
+    int rpc = FDW_CTA_ROWS;
     if (rpc_override > 0) {
         rpc = rpc_override;
     } else {
         const long long cap = (long long)nsm * cached_occupancy(kern, nthreads);
         /* small problems: shorten the chunks until the grid fills the machine twice over */
-        while (rpc > 2 && (long long)gx * ((rows + rpc - 1) / rpc) < 2 * cap) rpc /= 2;
+        while (rpc > 2 && (long long)gx * ((rows + rpc - 1) / rpc) < 2 * cap) rpc = (rpc + 1) / 2;
     }
     int gy = (rows + rpc - 1) / rpc;
     *grid = dim3(gx, gy < 1 ? 1 : gy, 1);
@@ -329,14 +332,16 @@ static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, co
     return FDW_OK;
 }
 
-/* A bulk rectangle whose width is not a multiple of the 256-thread CTA leaves the last CTA column
- * nearly empty while it still occupies a full residency slot for the whole launch (measured on the
- * 8192 x 4096 RTM grid, 1044 float4 columns: 5 CTA columns instead of 4.08 -> +24 % launch time).
- * Cut the ragged tail off into its own narrow rectangle; it runs on the side stream with the strips. */
+/* A bulk rectangle whose width is not a multiple of a WIDE CTA leaves the last CTA column nearly empty
+ * while it still occupies a residency slot for the whole launch (measured with 256-thread CTAs on the
+ * 8192 x 4096 RTM grid, 1044 float4 columns: 5 CTA columns instead of 4.08 -> +24 % launch time).  Cut
+ * the ragged tail off into its own narrow rectangle; it runs on the side stream with the strips.  With
+ * the default 64-thread CTAs the tail is at most one idle warp and nothing is cut. */
 static bool split_ragged_tail(const fdw_ctx *c, Rect *bulk, Rect *tail)
 {
-    const int n = bulk->c1 - bulk->c0, r = n % 256;
-    if (c->threads_override > 0 || n <= 256 || r == 0 || r > 128) return false;
+    const int w = c->threads_override > 0 ? c->threads_override : FDW_CTA_THREADS;
+    const int n = bulk->c1 - bulk->c0, r = n % w;
+    if (w < 256 || n <= w || r == 0 || r > w / 2) return false;
     *tail = *bulk;
     tail->c0 = bulk->c1 - r;
     bulk->c1 -= r;

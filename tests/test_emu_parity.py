@@ -66,9 +66,10 @@ def test_advance_wide_grid_many_chunks(emu, launch_mode):
 
 
 @pytest.mark.parametrize("taper", [TAPER_TOP, TAPER_NONE])
-def test_advance_ragged_bulk_tail(emu, launch_mode, taper):
+def test_advance_ragged_bulk_tail(emu, launch_mode, taper, monkeypatch):
     """more than one 256-thread CTA column plus a short remainder: the ragged tail of the bulk
     rectangle is launched as its own narrow rectangle (side stream when forking)"""
+    monkeypatch.setenv("FDW_THREADS", "256")  # the tail is only cut for wide CTAs (default: 64 threads)
     PC.case_advance(emu, FAMILY_GPU, RECIPE_G, taper, nx=40, nz=1300, nxb=10, nzb=12, nt=5)
 
 

@@ -76,8 +76,9 @@ def test_advance_medium_grid_many_ctas(lib):
 
 
 @pytest.mark.parametrize("taper", [TAPER_TOP, TAPER_NONE])
-def test_advance_ragged_bulk_tail(lib, launch_mode, taper):
+def test_advance_ragged_bulk_tail(lib, launch_mode, taper, monkeypatch):
     # > one 256-thread CTA column plus a short remainder: the bulk's ragged tail becomes its own rectangle
+    monkeypatch.setenv("FDW_THREADS", "256")  # the tail is only cut for wide CTAs (default: 64 threads)
     PC.case_advance(lib, FAMILY_GPU, RECIPE_G, taper, nx=40, nz=1300, nxb=10, nzb=12, nt=5)
     PC.case_advance(lib, FAMILY_GPU, RECIPE_G, taper, nx=1200, nz=4136, nxb=20, nzb=20, nt=4)  # the C4 width
 
