@@ -78,6 +78,9 @@ __device__ __forceinline__ void body(const Args& a,const float* P,float* PP,floa
 }
 
 __global__ void __launch_bounds__(256,4) k1(const __grid_constant__ Args a){ body<false>(a,a.p,a.pp,a.src_amp,blockIdx.x,blockIdx.y); }
+// register-budget variants for 64-thread CTAs: MINB CTAs/SM -> 65536/(64*MINB) registers per thread
+template<int MINB> __global__ void __launch_bounds__(64,MINB) k1r(const __grid_constant__ Args a){ body<false>(a,a.p,a.pp,a.src_amp,blockIdx.x,blockIdx.y); }
+typedef void (*k1fn)(const Args);
 
 struct DfArgs { Args a; float* bufA; float* bufB; float amp1, amp2; int nchunks, ntz, lag; unsigned* ticket; unsigned* done; int* err; };
 
@@ -144,6 +147,27 @@ int main(int argc,char**argv){
       float ms; cudaEventElapsedTime(&ms,e0,e1); if(rep>0&&ms<best) best=ms;
     }
     printf("K1 plain launches rpc=%2d            %.3f ms / 2 levels  %.1f Gpts/s\n",rpc,best/NPAIR,2.0*NPAIR*n*(double)n/(best*1e-3)/1e9); fflush(stdout);
+  }
+  // ---- register budget x geometry for 64-thread CTAs
+  if(argc>2 && !strcmp(argv[2],"regs")){
+    struct { const char* name; k1fn f; } rv[]={{"k1 (256,4) 64 regs",k1},{"k1r<16> 64 regs",k1r<16>},{"k1r<18> 56 regs",k1r<18>},{"k1r<20> 48 regs",k1r<20>},{"k1r<14> 72 regs",k1r<14>},{"k1r<12> 80 regs",k1r<12>}};
+    for(auto& v: rv) for(int rpc: {7,14}){
+      cudaFuncAttributes fa; cudaFuncGetAttributes(&fa,v.f);
+      dim3 grid((a.ncol4+63)/64,(n+rpc-1)/rpc), block(64); Args r=a; r.rows_per_cta=rpc;
+      float best=1e9;
+      for(int rep=0;rep<3;rep++){
+        cudaMemcpy(RA,A0,elems*4,cudaMemcpyDeviceToDevice); cudaMemcpy(RB,B0,elems*4,cudaMemcpyDeviceToDevice);
+        cudaEventRecord(e0);
+        for(int k=0;k<NPAIR;k++){
+          r.p=RA+o0; r.pp=RB+o0; r.src_amp=amp1; v.f<<<grid,block>>>(r);
+          r.p=RB+o0; r.pp=RA+o0; r.src_amp=amp2; v.f<<<grid,block>>>(r);
+        }
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms,e0,e1); if(rep>0&&ms<best) best=ms;
+      }
+      printf("%-22s regs=%3d spill=%4zu rpc=%2d  %.3f ms / 2 levels  %.1f Gpts/s\n",v.name,fa.numRegs,(size_t)fa.localSizeBytes,rpc,best/NPAIR,2.0*NPAIR*n*(double)n/(best*1e-3)/1e9); fflush(stdout);
+    }
+    return 0;
   }
   // ---- dataflow
   unsigned *ticket,*done; int* err; cudaMalloc(&ticket,4); cudaMalloc(&err,4); cudaMemset(err,0,4);
