@@ -237,11 +237,12 @@ static long long pitch_for(int nze) { return ((long long)nze + 4 + 31) / 32 * 32
 
 /* launch geometry: one thread per float4 column; CTAs tile z, x is cut into chunks of rows_per_cta
  * rows.  Measured on B200, interleaved in one process (tools/sweep_geometry.py, profiles/
- * r01_sweep_geometry.log): SMALL work units win -- 64-thread CTAs x 7 rows: 353 Gpts/s, 128 x 8: 339,
- * 256 x 32: 317 on the same GPU.  The 8 halo rows a chunk re-reads are L1/L2 hits, and with ~150 k short
- * CTAs per level neighbouring chunks run close together in time, so the L2 hit rate of those rows rises
- * (ncu: 41 % vs 33 %) and DRAM traffic falls from 1.05x to 0.99x of the algorithmic 16 B/point. */
-enum { FDW_CTA_THREADS = 64, FDW_CTA_ROWS = 7 };
+ * r01_sweep_geometry.log): SMALL work units win -- one-warp CTAs x 7 rows: 360 Gpts/s, 64 x 7: 354,
+ * 128 x 8: 339, 256 x 32: 317 on the same GPU(s).  The 8 halo rows a chunk re-reads are L1/L2 hits, and with
+ * ~300 k short CTAs per level neighbouring chunks run close together in time, so the L2 hit rate of those
+ * rows rises (ncu: 42 % vs 33 %) and DRAM traffic falls from 1.05x to 0.99x of the algorithmic 16 B/point.
+ * A warp is the natural unit of this kernel anyway: threads never exchange data or meet at a barrier. */
+enum { FDW_CTA_THREADS = 32, FDW_CTA_ROWS = 7 };
 static int cached_occupancy(const void *kern, int nthreads)
 {
     /* the occupancy query costs microseconds per call: remember it per (kernel, block size) */
@@ -270,6 +271,7 @@ static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int 
         /* small problems: shorten the chunks until the grid fills the machine twice over */
         while (rpc > 2 && (long long)gx * ((rows + rpc - 1) / rpc) < 2 * cap) rpc = (rpc + 1) / 2;
     }
+    while ((rows + rpc - 1) / rpc > 65535) rpc *= 2; /* gridDim.y limit */
     int gy = (rows + rpc - 1) / rpc;
     *grid = dim3(gx, gy < 1 ? 1 : gy, 1);
     *block = dim3(nthreads, 1, 1);

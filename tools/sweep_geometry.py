@@ -17,7 +17,7 @@ ve[:, n // 3: 2 * n // 3] = 3000.0
 ve[:, 2 * n // 3:] = 4000.0
 v2 = ve * ve
 srce = fdw.host.ricker_wavelet(10000, 0.001, 20.0, fdw.FAMILY_GPU)
-variants = [(32, 256), (8, 128), (7, 128), (6, 128), (8, 64), (7, 64), (6, 64), (7, 96), (14, 128), (11, 128), (13, 128)]
+variants = [(7, 64), (7, 32), (6, 32), (8, 32), (5, 64), (6, 64), (9, 64), (10, 64), (14, 64), (7, 128), (3, 64), (4, 64)]
 ctxs = {}
 for rpc, thr in variants:
     os.environ["FDW_ROWS_PER_CTA"], os.environ["FDW_THREADS"] = str(rpc), str(thr)
