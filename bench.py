@@ -38,6 +38,7 @@ DX = DZ = 10.0
 DT = 0.001
 FPEAK = 20.0
 FAC = 0.75
+STRONG = os.environ.get("FDW_BENCH_STRONG", "0") == "1"  # 1: the x extent stays NGRID for every N (strong scaling)
 HALO = os.environ.get("FDW_BENCH_HALO", "p2p")  # slab halo exchange at N>1: "p2p" (peer stores over NVLink) or "nccl"
 RECIPE = os.environ.get("FDW_BENCH_RECIPE", "G")  # "G" = bit-exact reference arithmetic (headline); "FAST" = FMA recipe
 BYTES_PER_POINT = 16  # read p, pp, v2*dt2 + write pp
@@ -209,6 +210,13 @@ def run_reference(args):
 
 
 def workload_config(ngpus):
+    if STRONG:
+        return {"workload": "synthetic 2D stencil propagator, %dx%d extended grid in total, cut into %d slab%s along x, "
+                            "order 8, recipe %s, top sponge, point source; %d time levels per step"
+                            % (NGRID, NGRID, ngpus, "s" if ngpus > 1 else "", RECIPE, LEVELS),
+                "grid": [NGRID, NGRID], "levels_per_step": LEVELS, "order": 8, "recipe": RECIPE,
+                "partition": "slab-x%d" % ngpus if ngpus > 1 else "single", "halo_exchange": HALO if ngpus > 1 else None,
+                "l2": "working set 3 GiB in total"}
     return {"workload": "synthetic 2D stencil propagator, %dx%d extended grid per GPU (x extent %d over %d slab%s), "
                         "order 8, recipe %s, top sponge, point source; %d time levels per step"
                         % (NGRID, NGRID, NGRID * ngpus, ngpus, "s" if ngpus > 1 else "",
@@ -241,7 +249,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    nxe_g, nze = NGRID * world, NGRID
+    nxe_g, nze = (NGRID if STRONG else NGRID * world), NGRID
     nb = NB
     nx, nz = nxe_g - 2 * nb, nze - 2 * nb
     srce = fdw.host.ricker_wavelet(10000, DT, FPEAK, fdw.FAMILY_GPU)
@@ -353,7 +361,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (one launch per level per GPU)
     peak, peak_src = peaks()
     per_launch_ms = ms / (args.steps * LEVELS)
-    launch_bytes = float(NGRID) * nze * BYTES_PER_POINT
+    launch_bytes = float(nloc) * nze * BYTES_PER_POINT  # rank 0's slab (= NGRID rows in the weak-scaling default)
     achieved = launch_bytes / (per_launch_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -377,7 +385,8 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if STRONG else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * field_bytes * world,
