@@ -68,6 +68,18 @@ struct Field {
     int pend = 0;          /* sponge multiplications not yet applied to the stored values */
 };
 
+/* One kernel launch of a time level, as recorded for the CUDA-graph replay of the level loop
+ * (fdw_peer_levels): what would have been launched, on which of the two streams, with which
+ * arguments.  kind 0 = step kernel (StepArgs by value), 1 = peer acquire-wait, 2 = peer release. */
+struct RecLaunch {
+    const void *kern = nullptr;
+    dim3 grid, block;
+    int side = 0, kind = 0, level = 0;
+    StepArgs a;
+    const unsigned *w_mine = nullptr; unsigned v = 0; int need_lo = 0, need_hi = 0; int *err = nullptr;
+    unsigned *s_lo = nullptr, *s_hi = nullptr;
+};
+
 struct fdw_ctx {
     fdw_params prm;
     int nxe, nze, gx0, nloc, H;
@@ -113,6 +125,17 @@ struct fdw_ctx {
     unsigned *flags_d = nullptr; /* written by the neighbours: [0] by the lower one, [1] by the upper one */
     unsigned peer_seq = 0;       /* boundary-row pushes issued so far (lock-step on all slabs) */
     long long peer_waits = 0;
+    /* CUDA-graph replay of the level loop: when `rec` is set, launches are recorded instead of issued */
+    std::vector<RecLaunch> *rec = nullptr;
+    int rec_level = 0;
+#ifndef FDW_EMU
+    cudaGraph_t lgraph = nullptr;
+    cudaGraphExec_t lexec = nullptr;
+    std::vector<cudaGraphNode_t> lnodes;   /* kernel nodes, in RecLaunch order */
+    std::vector<RecLaunch> lshape;         /* the launch list the graph was built from */
+#endif
+    int use_graph = 1;
+    long long graph_replays = 0;
     /* split-phase step (slab decomposition) */
     bool step_open = false;
     StepArgs step_args;
@@ -328,9 +351,16 @@ static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, co
     dim3 grid, block;
     launch_geometry(k, c->nsm, rc.c1 - rc.c0, rc.r1 - rc.r0, c->threads_override, c->rows_per_cta_override, &grid,
                     &block, &a.rows_per_cta);
+    c->launches++;
+    if (c->rec) {
+        RecLaunch r;
+        r.kern = k; r.grid = grid; r.block = block; r.side = st == c->side && st != c->stream; r.kind = 0;
+        r.level = c->rec_level; r.a = a;
+        c->rec->push_back(r);
+        return FDW_OK;
+    }
     void *params[] = {&a};
     CU(cudaLaunchKernel(k, grid, block, params, 0, st));
-    c->launches++;
     return FDW_OK;
 }
 
@@ -388,14 +418,15 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
     for (int k = 0; k < nside; k++) any_side = any_side || (side[k].c1 > side[k].c0 && side[k].r1 > side[k].r0);
     const bool do_fork = fork && any_side;
     cudaStream_t ss = do_fork ? c->side : st;
-    if (do_fork) {
+    const bool ev = do_fork && !c->rec; /* a recorded level gets its fork/join as graph edges instead */
+    if (ev) {
         CU(cudaEventRecord(c->ev_fork, st));
         CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
     }
     for (int k = 0; k < nside; k++) CHECK(launch_rect(c, base, recipe, epi, side[k], ss));
-    if (do_fork) CU(cudaEventRecord(c->ev_join, ss));
+    if (ev) CU(cudaEventRecord(c->ev_join, ss));
     CHECK(launch_rect(c, base, recipe, epi, bulk, st));
-    if (do_fork) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (ev) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     return FDW_OK;
 }
 
@@ -686,6 +717,7 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_PERSIST_LIMIT")) c->persist_limit = atoll(e);
     cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
+    if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
 
     /* coefficients and scalars: fd-code.cu:203-217 / fd.c:12-16 */
     float coefs[9];
@@ -777,6 +809,10 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fdw_peer_detach(c);
+#ifndef FDW_EMU
+    if (c->lexec) cudaGraphExecDestroy(c->lexec);
+    if (c->lgraph) cudaGraphDestroy(c->lgraph);
+#endif
     cudaFree(c->flags_d);
     for (int k = 0; k < 4; k++) cudaFree(c->f[k].base);
     cudaFree(c->vdt_base); cudaFree(c->tz_base); cudaFree(c->tx_base);
@@ -1376,10 +1412,18 @@ static int peer_wait(fdw_ctx *c, cudaStream_t st)
     if (!need_lo && !need_hi) return FDW_OK;
     const unsigned *mine = c->flags_d;
     unsigned v = c->peer_seq;
-    void *params[] = {&mine, &v, &need_lo, &need_hi, &c->errflag_d};
-    CU(cudaLaunchKernel(FDW_KPTR(k_peer_wait, thunk_peer_wait), dim3(1), dim3(1), params, 0, st));
     c->launches++;
     c->peer_waits++;
+    if (c->rec) {
+        RecLaunch r;
+        r.kern = FDW_KPTR(k_peer_wait, thunk_peer_wait); r.grid = dim3(1); r.block = dim3(1);
+        r.side = st == c->side && st != c->stream; r.kind = 1; r.level = c->rec_level;
+        r.w_mine = mine; r.v = v; r.need_lo = need_lo; r.need_hi = need_hi; r.err = c->errflag_d;
+        c->rec->push_back(r);
+        return FDW_OK;
+    }
+    void *params[] = {&mine, &v, &need_lo, &need_hi, &c->errflag_d};
+    CU(cudaLaunchKernel(FDW_KPTR(k_peer_wait, thunk_peer_wait), dim3(1), dim3(1), params, 0, st));
     return FDW_OK;
 }
 
@@ -1390,48 +1434,165 @@ static int peer_signal(fdw_ctx *c, cudaStream_t st)
     unsigned *flo = c->peer[0].on ? c->peer[0].flags + 1 : nullptr;
     unsigned *fhi = c->peer[1].on ? c->peer[1].flags + 0 : nullptr;
     unsigned v = c->peer_seq;
+    c->launches++;
+    if (c->rec) {
+        RecLaunch r;
+        r.kern = FDW_KPTR(k_peer_signal, thunk_peer_signal); r.grid = dim3(1); r.block = dim3(1);
+        r.side = st == c->side && st != c->stream; r.kind = 2; r.level = c->rec_level;
+        r.s_lo = flo; r.s_hi = fhi; r.v = v;
+        c->rec->push_back(r);
+        return FDW_OK;
+    }
     void *params[] = {&flo, &fhi, &v};
     CU(cudaLaunchKernel(FDW_KPTR(k_peer_signal, thunk_peer_signal), dim3(1), dim3(1), params, 0, st));
-    c->launches++;
     return FDW_OK;
 }
+
+/* one time level of the peer-memory slab loop: issued directly, or recorded (c->rec) */
+static int peer_level(fdw_ctx *c, int it)
+{
+    const int nc = c->ncol4;
+    CHECK(fdw_step_begin(c, it));
+    StepArgs a = c->step_args;
+    const int epi = phase_epi(c->phase);
+    const int wbuf = c->older[0]; /* the buffer this level is written to -- the same index on every slab */
+    a.push_lo = peer_image(c, 0, wbuf);
+    a.push_hi = peer_image(c, 1, wbuf);
+    a.push_nloc = c->nloc;
+    const int ilo = c->peer[0].on ? GUARD : 0, ihi = c->peer[1].on ? c->nloc - GUARD : c->nloc;
+    /* the boundary chain (acquire -> boundary strips with the push -> release) runs on the side
+     * stream, concurrently with the interior launch: a few microseconds of small kernels and the
+     * NVLink transfer hide behind the interior update.  Both join before the next level. */
+    const bool ev = !c->rec;
+    int rc = FDW_OK;
+    if (ev && (cudaEventRecord(c->ev_pfork, c->stream) != cudaSuccess ||
+               cudaStreamWaitEvent(c->side, c->ev_pfork, 0) != cudaSuccess))
+        rc = FDW_ERR_CUDA;
+    if (rc == FDW_OK) rc = peer_wait(c, c->side); /* the neighbours' rows of the newest level have landed */
+    for (int s = 0; s < 2 && rc == FDW_OK; s++) {
+        if (!c->peer[s].on) continue;
+        int r0 = s == 0 ? 0 : c->nloc - GUARD, r1 = s == 0 ? GUARD : c->nloc;
+        if (r0 < a.row0) r0 = a.row0;
+        if (r1 > a.row1) r1 = a.row1;
+        Rect strip = {0, nc, r0, r1, 1};
+        rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strip, c->side);
+    }
+    if (rc == FDW_OK) rc = peer_signal(c, c->side);
+    if (rc == FDW_OK && ev && cudaEventRecord(c->ev_pjoin, c->side) != cudaSuccess) rc = FDW_ERR_CUDA;
+    if (rc == FDW_OK) rc = launch_level(c, c->step_args, c->prm.recipe, epi, ilo, ihi, c->stream);
+    if (rc == FDW_OK && ev && cudaStreamWaitEvent(c->stream, c->ev_pjoin, 0) != cudaSuccess) rc = FDW_ERR_CUDA;
+    if (rc != FDW_OK) { c->step_open = false; return rc; }
+    return fdw_step_end(c);
+}
+
+#ifndef FDW_EMU
+/* CUDA-graph replay of the level loop.  A thin slab's level is ~100 us of GPU work but 13 driver calls
+ * (5 kernels, 4 event records, 4 stream waits): the host cannot enqueue them fast enough, the GPU starves
+ * (measured: 16384^2 over 8 GPUs, 136 us per level for 94 us of arithmetic).  Two consecutive levels are
+ * recorded (same bookkeeping, nothing launched), turned into one graph -- kernel nodes, the two streams'
+ * orders and the fork/join points as edges -- and every further pair of levels only refreshes the nodes'
+ * arguments (cudaGraphExecKernelNodeSetParams) and launches the graph once. */
+static void graph_drop(fdw_ctx *c)
+{
+    if (c->lexec) cudaGraphExecDestroy(c->lexec);
+    if (c->lgraph) cudaGraphDestroy(c->lgraph);
+    c->lexec = nullptr; c->lgraph = nullptr;
+    c->lnodes.clear(); c->lshape.clear();
+}
+
+static void node_params(RecLaunch &r, cudaKernelNodeParams *kp, void **slots)
+{
+    memset(kp, 0, sizeof *kp);
+    kp->func = const_cast<void *>(r.kern);
+    kp->gridDim = r.grid; kp->blockDim = r.block; kp->sharedMemBytes = 0; kp->extra = nullptr;
+    if (r.kind == 0) { slots[0] = &r.a; }
+    else if (r.kind == 1) { slots[0] = &r.w_mine; slots[1] = &r.v; slots[2] = &r.need_lo; slots[3] = &r.need_hi; slots[4] = &r.err; }
+    else { slots[0] = &r.s_lo; slots[1] = &r.s_hi; slots[2] = &r.v; }
+    kp->kernelParams = slots;
+}
+
+static bool same_shape(const std::vector<RecLaunch> &x, const std::vector<RecLaunch> &y)
+{
+    if (x.size() != y.size()) return false;
+    for (size_t i = 0; i < x.size(); i++)
+        if (x[i].kern != y[i].kern || x[i].side != y[i].side || x[i].level != y[i].level ||
+            x[i].grid.x != y[i].grid.x || x[i].grid.y != y[i].grid.y || x[i].block.x != y[i].block.x)
+            return false;
+    return true;
+}
+
+static int graph_build(fdw_ctx *c, std::vector<RecLaunch> &rec)
+{
+    graph_drop(c);
+    CU(cudaGraphCreate(&c->lgraph, 0));
+    cudaGraphNode_t start = nullptr; /* join of the previous level (empty node); none before the first */
+    int level = -1;
+    cudaGraphNode_t last[2] = {nullptr, nullptr};
+    auto close_level = [&]() -> int {
+        cudaGraphNode_t deps[2]; int nd = 0;
+        for (int s = 0; s < 2; s++) if (last[s]) deps[nd++] = last[s];
+        if (nd == 0) return FDW_OK;
+        CU(cudaGraphAddEmptyNode(&start, c->lgraph, deps, nd));
+        last[0] = last[1] = nullptr;
+        return FDW_OK;
+    };
+    for (size_t i = 0; i < rec.size(); i++) {
+        RecLaunch &r = rec[i];
+        if (r.level != level) { CHECK(close_level()); level = r.level; }
+        cudaKernelNodeParams kp; void *slots[5];
+        node_params(r, &kp, slots);
+        /* stream order within the level; the first node of each stream hangs off the previous level's join */
+        cudaGraphNode_t dep = last[r.side] ? last[r.side] : start;
+        cudaGraphNode_t node;
+        CU(cudaGraphAddKernelNode(&node, c->lgraph, dep ? &dep : nullptr, dep ? 1 : 0, &kp));
+        last[r.side] = node;
+        c->lnodes.push_back(node);
+    }
+    CHECK(close_level());
+    CU(cudaGraphInstantiate(&c->lexec, c->lgraph, 0));
+    c->lshape = rec;
+    return FDW_OK;
+}
+
+/* two levels (it, it+1): record, then build or refresh the graph and launch it */
+static int peer_level_pair_graph(fdw_ctx *c, int it)
+{
+    std::vector<RecLaunch> rec;
+    c->rec = &rec;
+    int rc = FDW_OK;
+    for (int l = 0; l < 2 && rc == FDW_OK; l++) { c->rec_level = l; rc = peer_level(c, it + l); }
+    c->rec = nullptr;
+    CHECK(rc);
+    if (!c->lexec || !same_shape(rec, c->lshape)) {
+        CHECK(graph_build(c, rec));
+    } else {
+        for (size_t i = 0; i < rec.size(); i++) {
+            cudaKernelNodeParams kp; void *slots[5];
+            node_params(rec[i], &kp, slots);
+            CU(cudaGraphExecKernelNodeSetParams(c->lexec, c->lnodes[i], &kp));
+        }
+    }
+    CU(cudaGraphLaunch(c->lexec, c->stream));
+    c->graph_replays++;
+    return FDW_OK;
+}
+#endif
 
 extern "C" int fdw_peer_levels(fdw_ctx *c, int it0, int nsteps)
 {
     if (!c || nsteps < 0) return FDW_ERR_ARG;
     if (!c->peer[0].on && !c->peer[1].on) { fdw_set_error("fdw_peer_levels: no neighbour attached"); return FDW_ERR_STATE; }
-    const int nc = c->ncol4;
-    for (int it = it0; it < it0 + nsteps; it++) {
-        CHECK(fdw_step_begin(c, it));
-        StepArgs a = c->step_args;
-        const int epi = phase_epi(c->phase);
-        const int wbuf = c->older[0]; /* the buffer this level is written to -- the same index on every slab */
-        a.push_lo = peer_image(c, 0, wbuf);
-        a.push_hi = peer_image(c, 1, wbuf);
-        a.push_nloc = c->nloc;
-        const int ilo = c->peer[0].on ? GUARD : 0, ihi = c->peer[1].on ? c->nloc - GUARD : c->nloc;
-        /* the boundary chain (acquire -> boundary strips with the push -> release) runs on the side
-         * stream, concurrently with the interior launch: a few microseconds of small kernels and the
-         * NVLink transfer hide behind the interior update.  Both join before the next level. */
-        int rc = FDW_OK;
-        if (cudaEventRecord(c->ev_pfork, c->stream) != cudaSuccess || cudaStreamWaitEvent(c->side, c->ev_pfork, 0) != cudaSuccess)
-            rc = FDW_ERR_CUDA;
-        if (rc == FDW_OK) rc = peer_wait(c, c->side); /* the neighbours' rows of the newest level have landed */
-        for (int s = 0; s < 2 && rc == FDW_OK; s++) {
-            if (!c->peer[s].on) continue;
-            int r0 = s == 0 ? 0 : c->nloc - GUARD, r1 = s == 0 ? GUARD : c->nloc;
-            if (r0 < a.row0) r0 = a.row0;
-            if (r1 > a.row1) r1 = a.row1;
-            Rect strip = {0, nc, r0, r1, 1};
-            rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strip, c->side);
-        }
-        if (rc == FDW_OK) rc = peer_signal(c, c->side);
-        if (rc == FDW_OK && cudaEventRecord(c->ev_pjoin, c->side) != cudaSuccess) rc = FDW_ERR_CUDA;
-        if (rc == FDW_OK) rc = launch_level(c, c->step_args, c->prm.recipe, epi, ilo, ihi, c->stream);
-        if (rc == FDW_OK && cudaStreamWaitEvent(c->stream, c->ev_pjoin, 0) != cudaSuccess) rc = FDW_ERR_CUDA;
-        if (rc != FDW_OK) { c->step_open = false; return rc; }
-        CHECK(fdw_step_end(c));
+    CHECK(bind(c));
+    int it = it0;
+    const int end = it0 + nsteps;
+#ifndef FDW_EMU
+    if (c->use_graph && nsteps >= 6) {
+        /* the first two levels directly (their sponge bookkeeping differs from the steady state) */
+        for (int k = 0; k < 2; k++) CHECK(peer_level(c, it++));
+        while (end - it >= 2) { CHECK(peer_level_pair_graph(c, it)); it += 2; }
     }
+#endif
+    while (it < end) CHECK(peer_level(c, it++));
     return FDW_OK;
 }
 
