@@ -74,7 +74,8 @@ struct Field {
 struct RecLaunch {
     const void *kern = nullptr;
     dim3 grid, block;
-    int side = 0, kind = 0, level = 0;
+    int side = 0, kind = 0, level = 0; /* side: 0 main stream, 1 boundary chain, 2 sponge strips (graph lanes) */
+    int par = 0;                       /* 1: independent of the previous launch of its lane (runs beside it) */
     StepArgs a;
     const unsigned *w_mine = nullptr; unsigned v = 0; int need_lo = 0, need_hi = 0; int *err = nullptr;
     unsigned *s_lo = nullptr, *s_hi = nullptr;
@@ -127,7 +128,7 @@ struct fdw_ctx {
     long long peer_waits = 0;
     /* CUDA-graph replay of the level loop: when `rec` is set, launches are recorded instead of issued */
     std::vector<RecLaunch> *rec = nullptr;
-    int rec_level = 0;
+    int rec_level = 0, rec_lane = -1, rec_par = 0;
 #ifndef FDW_EMU
     cudaGraph_t lgraph = nullptr;
     cudaGraphExec_t lexec = nullptr;
@@ -354,7 +355,9 @@ static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, co
     c->launches++;
     if (c->rec) {
         RecLaunch r;
-        r.kern = k; r.grid = grid; r.block = block; r.side = st == c->side && st != c->stream; r.kind = 0;
+        r.kern = k; r.grid = grid; r.block = block; r.kind = 0;
+        r.side = c->rec_lane >= 0 ? c->rec_lane : (st == c->side && st != c->stream);
+        r.par = c->rec_par;
         r.level = c->rec_level; r.a = a;
         c->rec->push_back(r);
         return FDW_OK;
@@ -423,7 +426,14 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
         CU(cudaEventRecord(c->ev_fork, st));
         CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
     }
-    for (int k = 0; k < nside; k++) CHECK(launch_rect(c, base, recipe, epi, side[k], ss));
+    if (c->rec && do_fork) c->rec_lane = 2;
+    for (int k = 0; k < nside; k++) {
+        if (c->rec && do_fork) c->rec_par = 1; /* disjoint rectangles of one level */
+        int rc = launch_rect(c, base, recipe, epi, side[k], ss);
+        c->rec_par = 0;
+        if (rc != FDW_OK) { c->rec_lane = -1; return rc; }
+    }
+    c->rec_lane = -1;
     if (ev) CU(cudaEventRecord(c->ev_join, ss));
     CHECK(launch_rect(c, base, recipe, epi, bulk, st));
     if (ev) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
@@ -1475,7 +1485,9 @@ static int peer_level(fdw_ctx *c, int it)
         if (r0 < a.row0) r0 = a.row0;
         if (r1 > a.row1) r1 = a.row1;
         Rect strip = {0, nc, r0, r1, 1};
+        if (c->rec && s == 1 && c->peer[0].on) c->rec_par = 1; /* the two boundary strips are independent */
         rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strip, c->side);
+        c->rec_par = 0;
     }
     if (rc == FDW_OK) rc = peer_signal(c, c->side);
     if (rc == FDW_OK && ev && cudaEventRecord(c->ev_pjoin, c->side) != cudaSuccess) rc = FDW_ERR_CUDA;
@@ -1515,7 +1527,7 @@ static bool same_shape(const std::vector<RecLaunch> &x, const std::vector<RecLau
 {
     if (x.size() != y.size()) return false;
     for (size_t i = 0; i < x.size(); i++)
-        if (x[i].kern != y[i].kern || x[i].side != y[i].side || x[i].level != y[i].level ||
+        if (x[i].kern != y[i].kern || x[i].side != y[i].side || x[i].par != y[i].par || x[i].level != y[i].level ||
             x[i].grid.x != y[i].grid.x || x[i].grid.y != y[i].grid.y || x[i].block.x != y[i].block.x)
             return false;
     return true;
@@ -1525,15 +1537,16 @@ static int graph_build(fdw_ctx *c, std::vector<RecLaunch> &rec)
 {
     graph_drop(c);
     CU(cudaGraphCreate(&c->lgraph, 0));
-    cudaGraphNode_t start = nullptr; /* join of the previous level (empty node); none before the first */
+    enum { NLANE = 3 };
+    cudaGraphNode_t start = nullptr;          /* join of the previous level (empty node); none before the first */
+    std::vector<cudaGraphNode_t> tails[NLANE]; /* frontier of each lane: what its next launch must wait for */
+    std::vector<cudaGraphNode_t> prev_deps[NLANE];
     int level = -1;
-    cudaGraphNode_t last[2] = {nullptr, nullptr};
     auto close_level = [&]() -> int {
-        cudaGraphNode_t deps[2]; int nd = 0;
-        for (int s = 0; s < 2; s++) if (last[s]) deps[nd++] = last[s];
-        if (nd == 0) return FDW_OK;
-        CU(cudaGraphAddEmptyNode(&start, c->lgraph, deps, nd));
-        last[0] = last[1] = nullptr;
+        std::vector<cudaGraphNode_t> deps;
+        for (int s = 0; s < NLANE; s++) { deps.insert(deps.end(), tails[s].begin(), tails[s].end()); tails[s].clear(); prev_deps[s].clear(); }
+        if (deps.empty()) return FDW_OK;
+        CU(cudaGraphAddEmptyNode(&start, c->lgraph, deps.data(), deps.size()));
         return FDW_OK;
     };
     for (size_t i = 0; i < rec.size(); i++) {
@@ -1541,11 +1554,18 @@ static int graph_build(fdw_ctx *c, std::vector<RecLaunch> &rec)
         if (r.level != level) { CHECK(close_level()); level = r.level; }
         cudaKernelNodeParams kp; void *slots[5];
         node_params(r, &kp, slots);
-        /* stream order within the level; the first node of each stream hangs off the previous level's join */
-        cudaGraphNode_t dep = last[r.side] ? last[r.side] : start;
+        const int ln = r.side;
+        /* lane order within the level; a lane's first node hangs off the previous level's join; a `par`
+         * node shares the dependencies of its predecessor and joins the lane's frontier beside it */
+        const bool beside = r.par && !tails[ln].empty();
+        std::vector<cudaGraphNode_t> deps;
+        if (beside) deps = prev_deps[ln];
+        else if (!tails[ln].empty()) deps = tails[ln];
+        else if (start) deps.push_back(start);
         cudaGraphNode_t node;
-        CU(cudaGraphAddKernelNode(&node, c->lgraph, dep ? &dep : nullptr, dep ? 1 : 0, &kp));
-        last[r.side] = node;
+        CU(cudaGraphAddKernelNode(&node, c->lgraph, deps.empty() ? nullptr : deps.data(), deps.size(), &kp));
+        if (beside) tails[ln].push_back(node);
+        else { prev_deps[ln] = deps; tails[ln].assign(1, node); }
         c->lnodes.push_back(node);
     }
     CHECK(close_level());
