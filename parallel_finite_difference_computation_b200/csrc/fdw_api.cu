@@ -124,6 +124,8 @@ struct fdw_ctx {
         int nloc = 0;
     } peer[2];                 /* [0] lower neighbour (rows below gx0), [1] upper neighbour */
     unsigned *flags_d = nullptr; /* written by the neighbours: [0] by the lower one, [1] by the upper one */
+    unsigned *pcount_d = nullptr; /* CTAs of the current level's boundary launches that have finished */
+    int fuse_flags = 1;          /* acquire/release inside the boundary kernels instead of separate launches */
     unsigned peer_seq = 0;       /* boundary-row pushes issued so far (lock-step on all slabs) */
     long long peer_waits = 0;
     /* CUDA-graph replay of the level loop: when `rec` is set, launches are recorded instead of issued */
@@ -365,6 +367,19 @@ static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, co
     void *params[] = {&a};
     CU(cudaLaunchKernel(k, grid, block, params, 0, st));
     return FDW_OK;
+}
+
+/* number of CTAs launch_rect will use for this rectangle (same geometry code) */
+static long long rect_ctas(fdw_ctx *c, int recipe, int epi, const Rect &rc)
+{
+    if (rc.c1 <= rc.c0 || rc.r1 <= rc.r0) return 0;
+    const void *k = step_kernel(c->prm.order, recipe, epi, rc.sponge);
+    if (!k) return 0;
+    dim3 grid, block;
+    int rpc;
+    launch_geometry(k, c->nsm, rc.c1 - rc.c0, rc.r1 - rc.r0, c->threads_override, c->rows_per_cta_override, &grid,
+                    &block, &rpc);
+    return (long long)grid.x * grid.y;
 }
 
 /* A bulk rectangle whose width is not a multiple of a WIDE CTA leaves the last CTA column nearly empty
@@ -728,6 +743,7 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
+    if (const char *e = getenv("FDW_FUSE_FLAGS")) c->fuse_flags = atoi(e);
 
     /* coefficients and scalars: fd-code.cu:203-217 / fd.c:12-16 */
     float coefs[9];
@@ -805,6 +821,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     TRY(cudaMalloc(&c->barrier_d, sizeof(unsigned)));
     TRY(cudaMalloc(&c->flags_d, 2 * sizeof(unsigned)));
     TRY(cudaMemsetAsync(c->flags_d, 0, 2 * sizeof(unsigned), c->stream));
+    TRY(cudaMalloc(&c->pcount_d, sizeof(unsigned)));
+    TRY(cudaMemsetAsync(c->pcount_d, 0, sizeof(unsigned), c->stream));
     TRY(cudaMalloc(&c->errflag_d, sizeof(int)));
     TRY(cudaMemsetAsync(c->errflag_d, 0, sizeof(int), c->stream));
     TRY(cudaStreamSynchronize(c->stream)); /* the staging vectors go out of scope */
@@ -824,6 +842,7 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     if (c->lgraph) cudaGraphDestroy(c->lgraph);
 #endif
     cudaFree(c->flags_d);
+    cudaFree(c->pcount_d);
     for (int k = 0; k < 4; k++) cudaFree(c->f[k].base);
     cudaFree(c->vdt_base); cudaFree(c->tz_base); cudaFree(c->tx_base);
     cudaFree(c->hist); cudaFree(c->img); cudaFree(c->dobs_d); cudaFree(c->rec_d);
@@ -1478,18 +1497,38 @@ static int peer_level(fdw_ctx *c, int it)
     if (ev && (cudaEventRecord(c->ev_pfork, c->stream) != cudaSuccess ||
                cudaStreamWaitEvent(c->side, c->ev_pfork, 0) != cudaSuccess))
         rc = FDW_ERR_CUDA;
-    if (rc == FDW_OK) rc = peer_wait(c, c->side); /* the neighbours' rows of the newest level have landed */
-    for (int s = 0; s < 2 && rc == FDW_OK; s++) {
+    Rect strips[2];
+    int nstrip = 0;
+    long long nctas = 0;
+    for (int s = 0; s < 2; s++) {
         if (!c->peer[s].on) continue;
         int r0 = s == 0 ? 0 : c->nloc - GUARD, r1 = s == 0 ? GUARD : c->nloc;
         if (r0 < a.row0) r0 = a.row0;
         if (r1 > a.row1) r1 = a.row1;
-        Rect strip = {0, nc, r0, r1, 1};
-        if (c->rec && s == 1 && c->peer[0].on) c->rec_par = 1; /* the two boundary strips are independent */
-        rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strip, c->side);
+        strips[nstrip] = Rect{0, nc, r0, r1, 1};
+        nctas += rect_ctas(c, c->prm.recipe, epi | fdw::EPI_PUSH, strips[nstrip]);
+        nstrip++;
+    }
+    /* acquire and release ride inside the boundary launches (two launches fewer on the critical path of a
+     * thin slab's level); with nothing to launch they fall back to the stand-alone kernels */
+    const bool fused = c->fuse_flags && nctas > 0;
+    if (fused) {
+        a.pw_flags = c->flags_d; a.pw_v = c->peer_seq; a.pw_lo = c->peer[0].on; a.pw_hi = c->peer[1].on;
+        a.pw_err = c->errflag_d;
+        c->peer_seq++;
+        a.ps_lo = c->peer[0].on ? c->peer[0].flags + 1 : nullptr; /* this slab is the lower neighbour's upper one */
+        a.ps_hi = c->peer[1].on ? c->peer[1].flags + 0 : nullptr;
+        a.ps_count = c->pcount_d; a.ps_v = c->peer_seq; a.ps_total = (unsigned)nctas;
+        c->peer_waits++;
+    } else if (rc == FDW_OK) {
+        rc = peer_wait(c, c->side); /* the neighbours' rows of the newest level have landed */
+    }
+    for (int s = 0; s < nstrip && rc == FDW_OK; s++) {
+        if (c->rec && s == 1) c->rec_par = 1; /* the two boundary strips are independent */
+        rc = launch_rect(c, a, c->prm.recipe, epi | fdw::EPI_PUSH, strips[s], c->side);
         c->rec_par = 0;
     }
-    if (rc == FDW_OK) rc = peer_signal(c, c->side);
+    if (rc == FDW_OK && !fused) rc = peer_signal(c, c->side);
     if (rc == FDW_OK && ev && cudaEventRecord(c->ev_pjoin, c->side) != cudaSuccess) rc = FDW_ERR_CUDA;
     if (rc == FDW_OK) rc = launch_level(c, c->step_args, c->prm.recipe, epi, ilo, ihi, c->stream);
     if (rc == FDW_OK && ev && cudaStreamWaitEvent(c->stream, c->ev_pjoin, 0) != cudaSuccess) rc = FDW_ERR_CUDA;

@@ -94,6 +94,16 @@ struct StepArgs {
      * neighbour's copy of the level being written (same pitch); null = no neighbour. */
     float *push_lo, *push_hi;
     int push_nloc;
+    /* acquire / release folded into the boundary launches (optional; null = done by separate kernels):
+     * every CTA first waits until the neighbours' "rows delivered" counters here reach pw_v, and the
+     * last CTA of the level's boundary launches (ps_total CTAs in all) raises this slab's counter in
+     * the neighbours' memory to ps_v after a system-scope fence. */
+    const unsigned *pw_flags;
+    unsigned pw_v;
+    int pw_lo, pw_hi;
+    int *pw_err;
+    unsigned *ps_lo, *ps_hi, *ps_count;
+    unsigned ps_v, ps_total;
 };
 
 /* the few quantities that change from one time level to the next; the ordinary kernels copy

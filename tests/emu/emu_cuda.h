@@ -35,6 +35,10 @@ extern int emu_levels; /* set by the caller before cudaLaunchCooperativeKernel *
 struct cudaDeviceProp { int multiProcessorCount; };
 
 #define __global__
+#define __device__
+#ifndef __forceinline__
+#define __forceinline__ inline
+#endif
 #define __grid_constant__
 #define __launch_bounds__(...)
 
