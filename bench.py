@@ -256,6 +256,8 @@ def run_ours(args):
     prop = fdist.SlabPropagator(nx, nz, nb, nb, DX, DZ, DT, order=8, fac=FAC, family=fdw.FAMILY_GPU,
                                 recipe=fdw.RECIPE_FAST if RECIPE == "FAST" else fdw.RECIPE_G,
                                 taper=fdw.TAPER_TOP, device=local_rank, rank=rank, world=world, halo=HALO)
+    if world > 1 and HALO == "p2p" and not prop.p2p:
+        globals()["HALO"] = "nccl"  # the slabs agreed to fall back (no peer access); report what actually ran
     # a non-default torch stream: the library launches on it, and the torch events below time it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -307,7 +309,7 @@ def run_ours(args):
     # other job's levels (double buffering, as a production caller would); the timed region still contains
     # every step's H2D and D2H copies.
     nloc = x1 - x0
-    pipelined = world == 1 or HALO == "p2p"
+    pipelined = world == 1 or prop.p2p
     props, bufs = [prop], []
     if pipelined:
         prop2 = fdist.SlabPropagator(nx, nz, nb, nb, DX, DZ, DT, order=8, fac=FAC, family=fdw.FAMILY_GPU,

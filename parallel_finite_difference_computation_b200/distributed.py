@@ -24,6 +24,7 @@ new, and neither changes the per-point arithmetic:
 rendezvous, the halo send/recv and the image reduction.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -79,6 +80,8 @@ class SlabPropagator:
             import torch
             self._comm_stream = torch.cuda.Stream(priority=-1)
             self._event = torch.cuda.Event()
+        if world > 1 and self.halo == "p2p":
+            self.attach_peers()  # collective; settles the exchange mechanism before first use
 
     # -- plumbing
     def close(self):
@@ -86,31 +89,57 @@ class SlabPropagator:
 
     def attach_peers(self):
         """halo="p2p": exchange the CUDA IPC handles of the slab buffers (all_gather over the
-        process group -- plumbing, once) and map the two neighbours' buffers"""
-        if self.world == 1 or self._attached:
+        process group -- plumbing, once) and map the two neighbours' buffers.  Collective.  If ANY
+        rank cannot map its neighbours (GPUs without peer access, IPC unavailable), every rank
+        drops back to halo="nccl" together -- a change of transport, same results -- and says so."""
+        if self.world == 1 or self._attached or self.halo != "p2p":
             return
+        import sys
+
+        import torch
         import torch.distributed as dist
-        mine = _lib.PeerInfo()
-        _lib.check(self.L, self.L.fdw_peer_export(self.h, C.byref(mine)))
+        if not self.on_gpu and not os.environ.get("FDW_TEST_FAIL_PEER_ATTACH"):
+            raise ValueError("halo='p2p' maps GPU buffers across processes; use halo='nccl' on the CPU")
+        ok, why, mine = 1, "", _lib.PeerInfo()
+        try:
+            if os.environ.get("FDW_TEST_FAIL_PEER_ATTACH") == str(self.rank):
+                raise _lib.FdwError(-2, "peer attach failure injected by FDW_TEST_FAIL_PEER_ATTACH")
+            _lib.check(self.L, self.L.fdw_peer_export(self.h, C.byref(mine)))
+        except _lib.FdwError as e:
+            ok, why = 0, str(e)
         infos = [None] * self.world
-        dist.all_gather_object(infos, bytes(mine))
-        lo = _lib.PeerInfo.from_buffer_copy(infos[self.rank - 1]) if self.rank > 0 else None
-        hi = _lib.PeerInfo.from_buffer_copy(infos[self.rank + 1]) if self.rank < self.world - 1 else None
-        _lib.check(self.L, self.L.fdw_peer_attach(self.h, C.byref(lo) if lo else None, C.byref(hi) if hi else None))
-        dist.barrier()  # nobody pushes before every slab has zeroed its flags
+        dist.all_gather_object(infos, bytes(mine) if ok else None)
+        if ok and all(i is not None for i in infos) and not os.environ.get("FDW_TEST_FAIL_PEER_ATTACH"):
+            lo = _lib.PeerInfo.from_buffer_copy(infos[self.rank - 1]) if self.rank > 0 else None
+            hi = _lib.PeerInfo.from_buffer_copy(infos[self.rank + 1]) if self.rank < self.world - 1 else None
+            try:
+                _lib.check(self.L, self.L.fdw_peer_attach(self.h, C.byref(lo) if lo else None,
+                                                          C.byref(hi) if hi else None))
+            except _lib.FdwError as e:
+                ok, why = 0, str(e)
+        else:
+            ok = 0
+        agree = torch.tensor([ok], dtype=torch.int32, device="cuda" if self.on_gpu else "cpu")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)  # also the barrier: nobody pushes before every slab has zeroed its flags
+        if int(agree.item()) == 0:
+            self.L.fdw_peer_detach(self.h)
+            self.halo = "nccl"
+            if why or self.rank == 0:
+                print("fdwave: peer-memory halo exchange unavailable (%s); all slabs use NCCL send/recv"
+                      % (why or "a neighbour could not map its peers"), file=sys.stderr)
+            return
         self._attached = True
 
     def _peer_refresh(self):
         """after this slab's buffers were zeroed or uploaded: push the newest level's boundary rows
         and raise the flag; the neighbours' first boundary launch of the next level waits for it
         (so it can never push into a buffer that is still to be zeroed)"""
-        self.attach_peers()
         _lib.check(self.L, self.L.fdw_peer_refresh(self.h))
         _lib.check(self.L, self.L.fdw_peer_fence(self.h))
 
     @property
     def p2p(self):
-        return self.world > 1 and self.on_gpu and self.halo == "p2p"
+        return self.world > 1 and self.halo == "p2p" and self._attached
 
     def set_stream(self, cuda_stream):
         self.w.set_stream(cuda_stream)
@@ -254,7 +283,6 @@ class SlabPropagator:
                 _lib.check(L, L.fdw_step_end(h))
             return
         if self.p2p:
-            self.attach_peers()
             _lib.check(L, L.fdw_peer_levels(h, it0, nsteps))
             _lib.check(L, L.fdw_peer_fence(h))
             return

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, family, taper, outdir):
+def _worker(rank, world, port, family, taper, outdir, halo=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -44,8 +44,12 @@ def _worker(rank, world, port, family, taper, outdir):
     fam_o = O.FAM_G if family == FAMILY_GPU else O.FAM_C
     srce = O.ricker_wavelet(nt, 0.001, 30.0, fam_o)
     fac = 0.6 if family == FAMILY_GPU else 0.11
+    if halo == "p2p":  # the peer mapping fails on rank 1: every slab must fall back to send/recv together
+        os.environ["FDW_TEST_FAIL_PEER_ATTACH"] = "1"
     sp = D.SlabPropagator(nx, nz, nxb, nzb, 10.0, 12.5, 0.001, rank=rank, world=world, lib=emu, on_gpu=False,
-                          order=8, fac=fac, family=family, taper=taper, nt=nt)
+                          order=8, fac=fac, family=family, taper=taper, nt=nt, halo=halo)
+    if halo == "p2p":
+        assert sp.halo == "nccl" and not sp.p2p
     x0, x1 = sp.slab
     sp.set_v2_local(v2[x0:x1])
     sp.set_wavelet(srce)
@@ -95,6 +99,39 @@ def test_slab_matches_single_domain_bitwise(tmp_path, world, family, taper):
     older = np.concatenate([np.load(tmp_path / ("older_%d.npy" % r)) for r in range(world)])
     PC.assert_bit_equal(newest, a, "slab newest world=%d" % world)
     PC.assert_bit_equal(older, b, "slab older world=%d" % world)
+
+
+def test_peer_mapping_failure_falls_back_to_send_recv_on_every_rank(tmp_path):
+    """halo='p2p' requested, one rank cannot map its neighbours: the slabs agree (all_reduce) to use
+    send/recv instead; the result is still the single-domain one bit for bit"""
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_cases as PC
+    from emu_loader import load as load_emu
+    from oracle import oracle as O
+    from parallel_finite_difference_computation_b200 import FAMILY_GPU, SRC_POINT, TAPER_TOP, Wave2D
+
+    emu = load_emu()
+    world = 3
+    mp.spawn(_worker, args=(world, _free_port(), FAMILY_GPU, TAPER_TOP, str(tmp_path), "p2p"), nprocs=world, join=True)
+    rng = np.random.default_rng(42)
+    nx, nz, nxb, nzb, nt = 53, 37, 9, 8, 14
+    nxe, nze = nx + 2 * nxb, nz + 2 * nzb
+    v2 = PC.layered_v2(nx, nz, nxb, nzb, rng)
+    a = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    b = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    srce = O.ricker_wavelet(nt, 0.001, 30.0, O.FAM_G)
+    with Wave2D(nx, nz, nxb, nzb, 10.0, 12.5, 0.001, order=8, fac=0.6, family=FAMILY_GPU, taper=TAPER_TOP, nt=nt,
+                lib=emu) as w:
+        w.set_v2(v2)
+        w.set_wavelet(srce)
+        w.set_source(nxb + nx // 2, nzb + 1, SRC_POINT)
+        w.propagate(a, b, 0, nt)
+    newest = np.concatenate([np.load(tmp_path / ("newest_%d.npy" % r)) for r in range(world)])
+    older = np.concatenate([np.load(tmp_path / ("older_%d.npy" % r)) for r in range(world)])
+    PC.assert_bit_equal(newest, a, "fallback newest")
+    PC.assert_bit_equal(older, b, "fallback older")
 
 
 def test_partitions():
