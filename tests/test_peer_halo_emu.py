@@ -162,3 +162,33 @@ def test_peer_protocol_errors(emu):
     finally:
         for w in (a, b, c):
             w.close()
+
+
+def test_async_local_round_trip_equals_synchronous(emu):
+    """propagate_local_async (upload, levels and download enqueued without a final synchronisation; the
+    building block of the double-buffered end-to-end loop in bench.py) gives what propagate_local gives"""
+    from parallel_finite_difference_computation_b200 import distributed as D
+    rng = np.random.default_rng(5)
+    nx, nz, nb, nt = 33, 27, 8, 9
+    nxe, nze = nx + 2 * nb, nz + 2 * nb
+    v2 = PC.layered_v2(nx, nz, nb, nb, rng)
+    a = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    b = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    srce = O.ricker_wavelet(nt, 0.001, 30.0, O.FAM_G)
+    outs = []
+    for use_async in (False, True):
+        sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, lib=emu, on_gpu=False, order=8, fac=0.6,
+                              family=FAMILY_GPU, taper=TAPER_TOP, nt=nt)
+        sp.set_v2_local(v2)
+        sp.set_wavelet(srce)
+        sp.set_source(nb + 11, nb + 2, SRC_POINT)
+        x, y = a.copy(), b.copy()
+        if use_async:
+            sp.propagate_local_async(x, y, 0, nt)
+            sp.sync()
+        else:
+            sp.propagate_local(x, y, 0, nt)
+        outs.append((x, y))
+        sp.close()
+    PC.assert_bit_equal(outs[1][0], outs[0][0], "async newest")
+    PC.assert_bit_equal(outs[1][1], outs[0][1], "async older")
