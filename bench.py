@@ -320,7 +320,11 @@ def run_ours(args):
         prop2.set_v2_local(v2_local)
         prop2.set_wavelet(srce)
         prop2.set_source(nxe_g // 2, nb)
-        props.append(prop2)
+        if world == 1 or prop2.p2p:
+            props.append(prop2)
+        else:  # (cannot happen if the first one attached; be safe) one step at a time
+            prop2.close()
+            pipelined = False
     for _ in props:
         hn = torch.zeros((nloc, nze), dtype=torch.float32).pin_memory()
         ho = torch.zeros((nloc, nze), dtype=torch.float32).pin_memory()
