@@ -131,12 +131,10 @@ struct fdw_ctx {
     /* CUDA-graph replay of the level loop: when `rec` is set, launches are recorded instead of issued */
     std::vector<RecLaunch> *rec = nullptr;
     int rec_level = 0, rec_lane = -1, rec_par = 0;
-#ifndef FDW_EMU
     cudaGraph_t lgraph = nullptr;
     cudaGraphExec_t lexec = nullptr;
     std::vector<cudaGraphNode_t> lnodes;   /* kernel nodes, in RecLaunch order */
     std::vector<RecLaunch> lshape;         /* the launch list the graph was built from */
-#endif
     int use_graph = 1;
     long long graph_replays = 0;
     /* split-phase step (slab decomposition) */
@@ -180,6 +178,8 @@ __global__ void k_peer_signal(unsigned *flag_lo, unsigned *flag_hi, unsigned v)
 {
 #ifndef FDW_EMU
     __threadfence_system();
+#else
+    __sync_synchronize();
 #endif
     if (flag_lo) *(volatile unsigned *)flag_lo = v;
     if (flag_hi) *(volatile unsigned *)flag_hi = v;
@@ -192,7 +192,7 @@ __global__ void k_peer_wait(const unsigned *mine, unsigned v, int need_lo, int n
 {
 #ifdef FDW_EMU
     /* the host stand-in runs everything synchronously: an unmet flag is a protocol error */
-    if ((need_lo && mine[0] < v) || (need_hi && mine[1] < v)) *error_flag = 2;
+    if ((need_lo && !emu_wait_flag(mine + 0, v)) || (need_hi && !emu_wait_flag(mine + 1, v))) *error_flag = 2;
 #else
     const long long t0 = clock64();
     for (int s = 0; s < 2; s++) {
@@ -837,10 +837,8 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     fdw_peer_detach(c);
-#ifndef FDW_EMU
     if (c->lexec) cudaGraphExecDestroy(c->lexec);
     if (c->lgraph) cudaGraphDestroy(c->lgraph);
-#endif
     cudaFree(c->flags_d);
     cudaFree(c->pcount_d);
     for (int k = 0; k < 4; k++) cudaFree(c->f[k].base);
@@ -1536,7 +1534,6 @@ static int peer_level(fdw_ctx *c, int it)
     return fdw_step_end(c);
 }
 
-#ifndef FDW_EMU
 /* CUDA-graph replay of the level loop.  A thin slab's level is ~100 us of GPU work but 13 driver calls
  * (5 kernels, 4 event records, 4 stream waits): the host cannot enqueue them fast enough, the GPU starves
  * (measured: 16384^2 over 8 GPUs, 136 us per level for 94 us of arithmetic).  Two consecutive levels are
@@ -1560,6 +1557,13 @@ static void node_params(RecLaunch &r, cudaKernelNodeParams *kp, void **slots)
     else if (r.kind == 1) { slots[0] = &r.w_mine; slots[1] = &r.v; slots[2] = &r.need_lo; slots[3] = &r.need_hi; slots[4] = &r.err; }
     else { slots[0] = &r.s_lo; slots[1] = &r.s_hi; slots[2] = &r.v; }
     kp->kernelParams = slots;
+#ifdef FDW_EMU
+    /* the host stand-in has to copy the argument values; it is told their sizes through `extra` */
+    static size_t sz_step[] = {sizeof(StepArgs), 0};
+    static size_t sz_wait[] = {sizeof(const unsigned *), sizeof(unsigned), sizeof(int), sizeof(int), sizeof(int *), 0};
+    static size_t sz_signal[] = {sizeof(unsigned *), sizeof(unsigned *), sizeof(unsigned), 0};
+    kp->extra = (void **)(r.kind == 0 ? sz_step : r.kind == 1 ? sz_wait : sz_signal);
+#endif
 }
 
 static bool same_shape(const std::vector<RecLaunch> &x, const std::vector<RecLaunch> &y)
@@ -1635,7 +1639,6 @@ static int peer_level_pair_graph(fdw_ctx *c, int it)
     c->graph_replays++;
     return FDW_OK;
 }
-#endif
 
 extern "C" int fdw_peer_levels(fdw_ctx *c, int it0, int nsteps)
 {
@@ -1644,13 +1647,11 @@ extern "C" int fdw_peer_levels(fdw_ctx *c, int it0, int nsteps)
     CHECK(bind(c));
     int it = it0;
     const int end = it0 + nsteps;
-#ifndef FDW_EMU
     if (c->use_graph && nsteps >= 6) {
         /* the first two levels directly (their sponge bookkeeping differs from the steady state) */
         for (int k = 0; k < 2; k++) CHECK(peer_level(c, it++));
         while (end - it >= 2) { CHECK(peer_level_pair_graph(c, it)); it += 2; }
     }
-#endif
     while (it < end) CHECK(peer_level(c, it++));
     return FDW_OK;
 }

@@ -2,6 +2,7 @@
 #include "emu_cuda.h"
 
 #include <stdint.h>
+#include <vector>
 #include <time.h>
 
 thread_local uint3_emu blockIdx, threadIdx;
@@ -85,3 +86,77 @@ cudaError_t cudaDeviceGetAttribute(int *value, int, int) { *value = 1; return cu
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+
+/* ---- CUDA graphs (see emu_cuda.h) */
+struct emu_node {
+    bool kernel = false;
+    void *func = nullptr;
+    dim3 grid, block;
+    std::vector<std::vector<unsigned char>> args;
+    void set(const cudaKernelNodeParams *p)
+    {
+        func = p->func; grid = p->gridDim; block = p->blockDim;
+        const size_t *sz = (const size_t *)p->extra;
+        args.clear();
+        for (int i = 0; sz && sz[i]; i++) {
+            const unsigned char *src = (const unsigned char *)p->kernelParams[i];
+            args.emplace_back(src, src + sz[i]);
+        }
+    }
+};
+struct emu_graph { std::vector<emu_node *> nodes; bool exec = false; };
+long long emu_graph_launches = 0;
+
+cudaError_t cudaGraphCreate(cudaGraph_t *g, unsigned) { *g = new emu_graph(); return cudaSuccess; }
+cudaError_t cudaGraphDestroy(cudaGraph_t g)
+{
+    if (g) { for (emu_node *n : g->nodes) delete n; delete g; }
+    return cudaSuccess;
+}
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; } /* shares the graph's nodes */
+cudaError_t cudaGraphAddEmptyNode(cudaGraphNode_t *n, cudaGraph_t g, const cudaGraphNode_t *, size_t)
+{
+    *n = new emu_node();
+    g->nodes.push_back(*n);
+    return cudaSuccess;
+}
+cudaError_t cudaGraphAddKernelNode(cudaGraphNode_t *n, cudaGraph_t g, const cudaGraphNode_t *deps, size_t nd,
+                                   const cudaKernelNodeParams *p)
+{
+    for (size_t i = 0; i < nd; i++) { /* every dependency must already exist: creation order is a topological order */
+        bool found = false;
+        for (emu_node *m : g->nodes) found = found || m == deps[i];
+        if (!found) return 1;
+    }
+    *n = new emu_node();
+    (*n)->kernel = true;
+    (*n)->set(p);
+    g->nodes.push_back(*n);
+    return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned long long)
+{
+    *e = new emu_graph();
+    (*e)->nodes = g->nodes; /* same node objects: SetParams on the exec updates what Launch runs */
+    (*e)->exec = true;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphExecKernelNodeSetParams(cudaGraphExec_t, cudaGraphNode_t n, const cudaKernelNodeParams *p)
+{
+    if (!n->kernel || n->func != p->func || n->grid.x != p->gridDim.x || n->grid.y != p->gridDim.y ||
+        n->block.x != p->blockDim.x)
+        return 1; /* the real API rejects a change of kernel; be at least as strict */
+    n->set(p);
+    return cudaSuccess;
+}
+cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t st)
+{
+    for (emu_node *n : e->nodes) {
+        if (!n->kernel) continue;
+        std::vector<void *> ptrs;
+        for (auto &a : n->args) ptrs.push_back(a.data());
+        cudaLaunchKernel(n->func, n->grid, n->block, ptrs.data(), 0, st);
+    }
+    emu_graph_launches++;
+    return cudaSuccess;
+}

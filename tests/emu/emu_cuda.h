@@ -73,6 +73,48 @@ cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **arg
 cudaError_t cudaLaunchCooperativeKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t);
 enum { cudaDevAttrCooperativeLaunch = 95 };
 cudaError_t cudaDeviceGetAttribute(int *value, int attr, int device);
+/* Acquire side of a flag in the host stand-in.  Default: kernels run synchronously in lock-step tests, so an
+ * unmet flag is a protocol error (returns false at once).  With FDW_EMU_SPIN=1 the slabs run in separate host
+ * threads, like GPUs, and the wait really waits (bounded: ~10 s). */
+#include <sched.h>
+#include <time.h>
+static inline bool emu_wait_flag(const volatile unsigned *f, unsigned v)
+{
+    if (*f >= v) { __sync_synchronize(); return true; }
+    const char *e = getenv("FDW_EMU_SPIN");
+    if (!e || e[0] != '1') return false;
+    struct timespec t0, t;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    while (*f < v) {
+        sched_yield();
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        if (t.tv_sec - t0.tv_sec > 10) return false;
+    }
+    __sync_synchronize();
+    return true;
+}
+
+/* CUDA graphs: kernel nodes are kept in creation order (the library creates them in a valid topological
+ * order) and a launch runs them one after the other.  Argument values are copied at node creation /
+ * update; their sizes arrive through cudaKernelNodeParams::extra (see node_params in fdw_api.cu). */
+struct cudaKernelNodeParams {
+    void *func; dim3 gridDim, blockDim; unsigned sharedMemBytes; void **kernelParams; void **extra;
+};
+struct emu_graph;
+struct emu_node;
+typedef emu_graph *cudaGraph_t;
+typedef emu_graph *cudaGraphExec_t;
+typedef emu_node *cudaGraphNode_t;
+cudaError_t cudaGraphCreate(cudaGraph_t *, unsigned);
+cudaError_t cudaGraphDestroy(cudaGraph_t);
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t);
+cudaError_t cudaGraphAddEmptyNode(cudaGraphNode_t *, cudaGraph_t, const cudaGraphNode_t *, size_t);
+cudaError_t cudaGraphAddKernelNode(cudaGraphNode_t *, cudaGraph_t, const cudaGraphNode_t *, size_t, const cudaKernelNodeParams *);
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long);
+cudaError_t cudaGraphExecKernelNodeSetParams(cudaGraphExec_t, cudaGraphNode_t, const cudaKernelNodeParams *);
+cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t);
+extern long long emu_graph_launches; /* for the tests: how many graph launches have run */
+
 /* "IPC" inside one process: the handle carries the pointer itself (two slab contexts of the
  * same test process can then push into each other's buffers) */
 struct cudaIpcMemHandle_t { char reserved[64]; };

@@ -192,3 +192,74 @@ def test_async_local_round_trip_equals_synchronous(emu):
         sp.close()
     PC.assert_bit_equal(outs[1][0], outs[0][0], "async newest")
     PC.assert_bit_equal(outs[1][1], outs[0][1], "async older")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_peer_level_loop_graph_replay_threads(emu, world, fuse, monkeypatch):
+    """The whole level loop in ONE fdw_peer_levels call per slab (as on the GPUs): the first two levels are issued
+    directly, every further pair is recorded, turned into a graph and replayed with refreshed node arguments
+    (the host stand-in keeps the kernel nodes and runs them in creation order).  Each slab runs in its own host
+    thread and the acquire really waits (FDW_EMU_SPIN), so the slabs are coupled only through the flags --
+    with the acquire/release inside the boundary kernels (fuse=1) and as stand-alone kernels (fuse=0)."""
+    import threading
+    monkeypatch.setenv("FDW_EMU_SPIN", "1")
+    monkeypatch.setenv("FDW_FUSE_FLAGS", fuse)
+    monkeypatch.setenv("FDW_GRAPH", "1")
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    rng = np.random.default_rng(23)
+    nx, nz, nxb, nzb, nt = 47, 33, 8, 8, 13  # 2 direct levels + 5 graph pairs + 1 direct level
+    nxe, nze = nx + 2 * nxb, nz + 2 * nzb
+    v2 = PC.layered_v2(nx, nz, nxb, nzb, rng)
+    a = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    b = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
+    srce = O.ricker_wavelet(nt, 0.001, 30.0, O.FAM_G)
+    kw = dict(order=8, fac=0.6, family=FAMILY_GPU, taper=TAPER_TOP, nt=nt, lib=emu)
+    with Wave2D(nx, nz, nxb, nzb, 10.0, 12.5, 0.001, **kw) as w:
+        w.set_v2(v2)
+        w.set_wavelet(srce)
+        w.set_source(nxb + nx // 2, nzb + 1, SRC_POINT)
+        ra, rb = a.copy(), b.copy()
+        w.propagate(ra, rb, 0, nt)
+    launches0 = C.c_longlong.in_dll(emu, "emu_graph_launches").value
+    slabs = [Wave2D(nx, nz, nxb, nzb, 10.0, 12.5, 0.001, slab=slab_rows(nxe, world, r), **kw) for r in range(world)]
+    try:
+        _attach_all(emu, slabs)
+        for r, w in enumerate(slabs):
+            x0, x1 = slab_rows(nxe, world, r)
+            _lib.check(emu, emu.fdw_set_v2_local(w.h, np.ascontiguousarray(v2[x0:x1])))
+            w.set_wavelet(srce)
+            w.set_source(nxb + nx // 2, nzb + 1, SRC_POINT)
+            _lib.check(emu, emu.fdw_fields_upload_local(w.h, 0, np.ascontiguousarray(a[x0:x1]),
+                                                        np.ascontiguousarray(b[x0:x1])))
+        for w in slabs:
+            _lib.check(emu, emu.fdw_peer_refresh(w.h))
+        errors = []
+
+        def run(w):
+            try:
+                _lib.check(emu, emu.fdw_peer_levels(w.h, 0, nt))
+                _lib.check(emu, emu.fdw_peer_fence(w.h))
+                w.sync()
+            except Exception as e:  # noqa: BLE001 -- reported by the main thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=run, args=(w,)) for w in slabs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(120)
+        assert not errors, errors
+        assert not any(t.is_alive() for t in threads)
+        assert C.c_longlong.in_dll(emu, "emu_graph_launches").value - launches0 == world * ((nt - 2) // 2)
+        for r, w in enumerate(slabs):
+            x0, x1 = slab_rows(nxe, world, r)
+            n = np.zeros((x1 - x0, nze), np.float32)
+            o = np.zeros((x1 - x0, nze), np.float32)
+            _lib.check(emu, emu.fdw_fields_download_local(w.h, 0, n.ctypes.data_as(C.c_void_p),
+                                                          o.ctypes.data_as(C.c_void_p)))
+            PC.assert_bit_equal(n, ra[x0:x1], "newest, slab %d/%d" % (r, world))
+            PC.assert_bit_equal(o, rb[x0:x1], "older, slab %d/%d" % (r, world))
+    finally:
+        for w in slabs:
+            w.close()
