@@ -716,8 +716,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     c->nloc = c->nxe;
     if (prm->slab_x1 > prm->slab_x0) {
         if (prm->slab_x0 < 0 || prm->slab_x1 > c->nxe) {
-            delete c;
             fdw_set_error("fdw_create: slab [%d,%d) outside [0,%d)", prm->slab_x0, prm->slab_x1, c->nxe);
+            delete c;
             return FDW_ERR_ARG;
         }
         c->gx0 = prm->slab_x0;
@@ -1550,7 +1550,7 @@ static void graph_drop(fdw_ctx *c)
 
 static void node_params(RecLaunch &r, cudaKernelNodeParams *kp, void **slots)
 {
-    memset(kp, 0, sizeof *kp);
+    *kp = cudaKernelNodeParams();
     kp->func = const_cast<void *>(r.kern);
     kp->gridDim = r.grid; kp->blockDim = r.block; kp->sharedMemBytes = 0; kp->extra = nullptr;
     if (r.kind == 0) { slots[0] = &r.a; }
