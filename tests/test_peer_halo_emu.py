@@ -263,3 +263,59 @@ def test_peer_level_loop_graph_replay_threads(emu, world, fuse, monkeypatch):
     finally:
         for w in slabs:
             w.close()
+
+
+def test_peer_rtm_main_shot_domain_divided_threads(emu, monkeypatch):
+    """config 5 in miniature: rtm_main's shot (forward with the history sharded over the slabs, backward with
+    back-injection and imaging) through the peer path, graph replay on, one host thread per slab"""
+    import threading
+    monkeypatch.setenv("FDW_EMU_SPIN", "1")
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    rng = np.random.default_rng(31)
+    nx, nz, nb, nt, world = 45, 31, 8, 12, 3
+    nxe = nx + 2 * nb
+    v2 = PC.layered_v2(nx, nz, nb, nb, rng)
+    srce = O.ricker_wavelet(nt, 0.001, 30.0, O.FAM_C)
+    dobs = rng.uniform(-1, 1, (1, nx, nt)).astype(np.float32)
+    sx, sz, gz = nb + nx // 2 - 2, nb + 1, nb
+    kw = dict(order=8, fac=0.11, family=FAMILY_CPU, recipe=_lib.RECIPE_C, taper=TAPER_TOP, nt=nt, history=True, lib=emu)
+    with Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, **kw) as w:
+        w.set_v2(v2)
+        w.set_wavelet(srce)
+        want = w.rtm_shot_cpu(sx, sz, gz, dobs, 0)
+    assert np.abs(want).max() > 0
+    slabs = [Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, slab=slab_rows(nxe, world, r), **kw) for r in range(world)]
+    try:
+        _attach_all(emu, slabs)
+        for r, w in enumerate(slabs):
+            x0, x1 = slab_rows(nxe, world, r)
+            _lib.check(emu, emu.fdw_set_v2_local(w.h, np.ascontiguousarray(v2[x0:x1])))
+            w.set_wavelet(srce)
+        rows, errors = [None] * world, []
+
+        def run(r, w):
+            try:
+                for phase, traces in ((_lib.PHASE_RTM_FWD, None), (_lib.PHASE_RTM_BWD, dobs)):
+                    ptr = traces.ctypes.data_as(C.c_void_p) if traces is not None else None
+                    _lib.check(emu, emu.fdw_shot_begin(w.h, phase, sx, sz, gz, ptr, 1, 0))
+                    _lib.check(emu, emu.fdw_peer_refresh(w.h))  # the phase zeroed the fields
+                    _lib.check(emu, emu.fdw_peer_fence(w.h))
+                    _lib.check(emu, emu.fdw_peer_levels(w.h, 0, nt))
+                    _lib.check(emu, emu.fdw_peer_fence(w.h))
+                d = w.devinfo()
+                out = np.zeros((max(d.nli, 1), nz), np.float32)
+                _lib.check(emu, emu.fdw_shot_end(w.h, out))
+                rows[r] = out[: d.nli]
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=run, args=(r, w)) for r, w in enumerate(slabs)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(120)
+        assert not errors, errors
+        PC.assert_bit_equal(np.concatenate(rows), want, "domain-divided image")
+    finally:
+        for w in slabs:
+            w.close()
