@@ -192,6 +192,10 @@ typedef struct fdw_halo {
 #define FDW_PHASE_RTM_BWD 3
 int fdw_shot_begin(fdw_ctx *ctx, int phase, int sx, int sz, int gz, const float *dobs_all, int ns, int is);
 int fdw_shot_end(fdw_ctx *ctx, float *out);
+/* all params.nt levels of the phase opened by fdw_shot_begin on a context that owns the whole grid
+ * (the time loops of mod_main.cpp:146-168 / rtm_main.cpp:166-188,196-220), asynchronous: together with
+ * fdw_mark_begin/end this gives the device time of a phase without its host transfers */
+int fdw_shot_run(fdw_ctx *ctx);
 int fdw_step_begin(fdw_ctx *ctx, int it);
 int fdw_step_rows(fdw_ctx *ctx, int row0, int row1, void *cuda_stream);
 int fdw_step_end(fdw_ctx *ctx);
@@ -248,6 +252,12 @@ int fdw_mark_begin(fdw_ctx *ctx);
 int fdw_mark_end(fdw_ctx *ctx, float *ms);
 /* number of kernels this context has launched so far */
 long long fdw_launch_count(fdw_ctx *ctx);
+/* other counters of the same kind (what actually ran: tests and benchmarks assert on them) */
+#define FDW_COUNTER_LAUNCHES 0
+#define FDW_COUNTER_GRAPH_REPLAYS 1   /* CUDA-graph replays of the peer-memory level loop */
+#define FDW_COUNTER_PERSIST_LAUNCHES 2 /* phases run by the persistent (L2-resident) kernel */
+#define FDW_COUNTER_TILE_LAUNCHES 3    /* phases run by the shared-memory tile kernel */
+long long fdw_counter(fdw_ctx *ctx, int which);
 /* standalone Laplacian on device-resident data of pair 0 (newest -> older), for benchmarks */
 int fdw_laplacian_device(fdw_ctx *ctx);
 

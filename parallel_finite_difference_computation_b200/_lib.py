@@ -18,6 +18,7 @@ RECIPE_G, RECIPE_C, RECIPE_FAST = 0, 1, 2
 TAPER_NONE, TAPER_TOP, TAPER_FOUR = 0, 1, 2
 SRC_POINT, SRC_GAUSS7 = 0, 1
 PHASE_PLAIN, PHASE_MODEL, PHASE_RTM_FWD, PHASE_RTM_BWD = 0, 1, 2, 3
+COUNTER_LAUNCHES, COUNTER_GRAPH_REPLAYS, COUNTER_PERSIST_LAUNCHES, COUNTER_TILE_LAUNCHES = 0, 1, 2, 3
 
 f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
@@ -114,6 +115,8 @@ SIGNATURES = {
     "fdw_mark_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "fdw_launch_count": (C.c_longlong, [C.c_void_p]),
     "fdw_laplacian_device": (C.c_int, [C.c_void_p]),
+    "fdw_counter": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "fdw_shot_run": (C.c_int, [C.c_void_p]),
 }
 
 

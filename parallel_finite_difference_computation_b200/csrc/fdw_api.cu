@@ -113,6 +113,7 @@ struct fdw_ctx {
     int coop = 0;                      /* device supports cooperative launches */
     long long persist_limit = 1LL << 18; /* float4 columns x rows below which phases run persistently */
     long long persist_launches = 0;
+    long long tile_launches = 0;
     int li0 = 0, nli = 0; /* interior x rows owned by this slab: global rows [li0, li0+nli) */
     /* split-phase shot state (slab decomposition) */
     int phase = 0, shot_gz = 0, shot_is = 0, shot_ns = 1;
@@ -312,6 +313,7 @@ static void base_args(const fdw_ctx *c, int pair, StepArgs *a)
     a->pp = o.r0;
     a->vdt = c->vdt;
     a->pitch = c->pitch;
+    a->apitch = c->pitch;
     a->col4_0 = 0;
     a->ncol4 = c->ncol4;
     a->grow0 = c->gx0;
@@ -321,6 +323,7 @@ static void base_args(const fdw_ctx *c, int pair, StepArgs *a)
     memcpy(a->cx, c->cx, sizeof a->cx);
     a->dz2inv = c->dz2inv;
     a->dx2inv = c->dx2inv;
+    a->one = 1.0f;
     a->taper_on = 0;
     a->np = n.pend;
     a->no = o.pend;
@@ -1173,6 +1176,15 @@ extern "C" int fdw_shot_end(fdw_ctx *c, float *out)
     return FDW_ERR_STATE;
 }
 
+extern "C" int fdw_shot_run(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    if (c->phase < PHASE_MODEL || c->phase > PHASE_RTM_BWD) { fdw_set_error("fdw_shot_run: no shot phase open"); return FDW_ERR_STATE; }
+    if (c->gx0 != 0 || c->nloc != c->nxe) { fdw_set_error("fdw_shot_run: slab contexts drive their levels with fdw_step_* / fdw_peer_levels"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    return phase_run(c, c->phase);
+}
+
 /* ------------------------------------------------------------------ stencil program */
 static int launch_lap(fdw_ctx *c, const float *src, float *dst)
 {
@@ -1711,3 +1723,15 @@ extern "C" int fdw_mark_end(fdw_ctx *c, float *ms)
 }
 
 extern "C" long long fdw_launch_count(fdw_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" long long fdw_counter(fdw_ctx *c, int which)
+{
+    if (!c) return 0;
+    switch (which) {
+    case FDW_COUNTER_LAUNCHES: return c->launches;
+    case FDW_COUNTER_GRAPH_REPLAYS: return c->graph_replays;
+    case FDW_COUNTER_PERSIST_LAUNCHES: return c->persist_launches;
+    case FDW_COUNTER_TILE_LAUNCHES: return c->tile_launches;
+    }
+    return 0;
+}

@@ -51,6 +51,7 @@ struct StepArgs {
     float *pp;       /* older level in, next level out (in place, own column only) */
     const float *vdt; /* fl32(v2*dt2), same layout */
     long long pitch; /* floats per row, multiple of 32, >= nze+4 */
+    long long apitch; /* row pitch of the history / image / halo-push targets (= pitch except in the tile kernel) */
     int col4_0;      /* first float4 column of this launch */
     int ncol4;       /* one past the last float4 column of this launch */
     int row0, row1;  /* local rows [row0,row1) handled by this launch */
@@ -60,6 +61,7 @@ struct StepArgs {
     int nze;         /* valid columns per row */
     float cz[9], cx[9]; /* G/FAST: premultiplied weights; C: both hold the raw weights */
     float dz2inv, dx2inv;
+    float one;        /* 1.0f, opaque to the assembler: the packed IEEE add is fma(acc, one, prod) */
     /* sponge */
     int taper_on;
     int np, no;       /* multiplications pending on the newer / older level (0..2) */
@@ -201,6 +203,39 @@ FDW_HD float leap(float p, float pp, float t)
 }
 #endif
 
+/* ---- packed FP32x2 arithmetic (sm_100a FMUL2 / FFMA2: two IEEE round-to-nearest results per
+ * instruction, each lane rounded exactly like the scalar FMUL / FADD, so the reference's --fmad=false
+ * bit pattern is kept while the FP32 issue slots halve).  ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+ * into one FFMA2 even under --fmad=false (checked in SASS), which would change the rounding; the
+ * accumulate step is therefore written as fma(acc, one, prod) with `one` = 1.0f passed as a kernel
+ * argument the assembler cannot see through: acc*1+prod rounds once, i.e. it IS the IEEE add, and an
+ * FFMA2 cannot absorb a second multiply. */
+#ifdef __CUDA_ARCH__
+typedef unsigned long long f2;
+FDW_HD f2 pk(float a, float b) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+FDW_HD float lo2(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+FDW_HD float hi2(f2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+FDW_HD f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+FDW_HD f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#else
+struct f2 { float a, b; };
+FDW_HD f2 pk(float a, float b) { f2 r = {a, b}; return r; }
+FDW_HD float lo2(f2 v) { return v.a; }
+FDW_HD float hi2(f2 v) { return v.b; }
+FDW_HD f2 mul2(f2 a, f2 b) { return pk(a.a * b.a, a.b * b.b); }
+FDW_HD f2 fma2(f2 a, f2 b, f2 c) { return pk(fmaf(a.a, b.a, c.a), fmaf(a.b, b.b, c.b)); }
+#endif
+FDW_HD f2 bc2(float c) { return pk(c, c); }
+/* product of the z-row pair (za[i], za[i+1]) with one weight.  Even i: the pair is an aligned register
+ * pair of a float4 load, one FMUL2.  Odd i: the two floats sit in different register pairs, so two scalar
+ * FMULs write straight into a fresh aligned pair (no MOVs, no extra live registers); same value per lane. */
+FDW_HD f2 zprod(const float *za, int i, float c)
+{
+    return (i & 1) ? pk(fmul(za[i], c), fmul(za[i + 1], c)) : mul2(pk(za[i], za[i + 1]), bc2(c));
+}
+/* IEEE add of two packed pairs: a*1 + b, one rounding (see above) */
+FDW_HD f2 add2(f2 a, f2 one, f2 b) { return fma2(a, one, b); }
+
 template <int K> FDW_HD float get(const float4 &v) { return K == 0 ? v.x : K == 1 ? v.y : K == 2 ? v.z : v.w; }
 FDW_HD float getk(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
@@ -241,7 +276,210 @@ float4 add_source(const StepArgs &a, float src_amp, float4 r4, int gi, int j0)
     return make_float4(res[0], res[1], res[2], res[3]);
 }
 
-template <int ORDER, int RECIPE, bool TAPER, int EPI>
+/* Everything of ONE ROW of one thread's float4 column once its operands are in registers: Laplacian in the
+ * selected recipe, leapfrog update, source patch, trace back-injection.  w[] is the rotating x window of the
+ * newer level (w[(u+io)%W] = row lr-H+io), l4 / r4 the aligned float4 left and right of the centre row, o4 the
+ * older level, v4 = fl32(v2*dt2).  Shared by the global-memory kernels (step_thread) and the shared-memory tile
+ * kernel (tile_thread): the arithmetic and its order exist once. */
+template <int ORDER, int RECIPE, int EPI, bool PACKED>
+FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[ORDER + 1], const int u, const float4 l4,
+                         const float4 r4, const float4 o4, const float4 v4, const int gi, const int j0, const bool ring,
+                         const bool near_src)
+{
+    constexpr int H = ORDER / 2, W = ORDER + 1;
+    const float4 c4 = w[(u + H) % W];
+    const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
+    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+    const float oo[4] = {o4.x, o4.y, o4.z, o4.w};
+    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+    float lap[4], res[4];
+        if (!PACKED) {
+            /* scalar arithmetic (round 1): kept for A/B measurements and as the readable statement
+             * of the per-point operation sequence; the packed path below is bit-identical */
+            FDW_UNROLL
+            for (int k = 0; k < 4; k++) {
+                if (RECIPE == RECIPE_G) {
+                    float az = fmul(za[4 + k - H], a.cz[0]);
+                    float ax = fmul(getk(w[(u + 0) % W], k), a.cx[0]);
+                    FDW_UNROLL
+                    for (int io = 1; io <= ORDER; io++) {
+                        az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
+                        ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
+                    }
+                    lap[k] = fadd(az, ax);
+                } else if (RECIPE == RECIPE_C) {
+                    float acm = fmul(fmul(za[4 + k - H], a.cz[0]), a.dz2inv);
+                    acm = fadd(acm, fmul(fmul(getk(w[(u + 0) % W], k), a.cx[0]), a.dx2inv));
+                    FDW_UNROLL
+                    for (int io = 1; io <= ORDER; io++) {
+                        acm = fadd(acm, fmul(fmul(za[4 + k - H + io], a.cz[io]), a.dz2inv));
+                        acm = fadd(acm, fmul(fmul(getk(w[(u + io) % W], k), a.cx[io]), a.dx2inv));
+                    }
+                    lap[k] = acm;
+                } else {
+                    float sm = fmul(cc[k], a.cz[H] + a.cx[H]);
+                    FDW_UNROLL
+                    for (int d = 1; d <= H; d++) {
+                        sm = ffma(a.cz[H + d], za[4 + k - d] + za[4 + k + d], sm);
+                        sm = ffma(a.cx[H + d], getk(w[(u + H - d) % W], k) + getk(w[(u + H + d) % W], k), sm);
+                    }
+                    lap[k] = sm;
+                }
+            }
+        } else {
+            /* two packed pairs per float4: points (0,1) and (2,3).  Per lane the operation
+             * sequence is the scalar one of the reference, only two lanes share an instruction. */
+            const f2 one = bc2(a.one);
+            constexpr int B = 4 - H; /* za index of the first z tap of point 0 */
+            f2 l01, l23;
+            if (RECIPE == RECIPE_G) {
+                /* two accumulators, ascending io, summed last (fd-code.cu:66-72).
+                 * The reference's "0 +" first add is dropped: it can only change
+                 * the sign of an all-zero sum, which provably never reaches pp. */
+                f2 az0 = zprod(za, B, a.cz[0]);
+                f2 az1 = zprod(za, B + 2, a.cz[0]);
+                FDW_UNROLL
+                for (int io = 1; io <= ORDER; io++) { /* z first: l4 / r4 die here */
+                    az0 = add2(az0, one, zprod(za, B + io, a.cz[io]));
+                    az1 = add2(az1, one, zprod(za, B + io + 2, a.cz[io]));
+                }
+                f2 ax0 = mul2(pk(w[u % W].x, w[u % W].y), bc2(a.cx[0]));
+                f2 ax1 = mul2(pk(w[u % W].z, w[u % W].w), bc2(a.cx[0]));
+                FDW_UNROLL
+                for (int io = 1; io <= ORDER; io++) {
+                    const float4 &wx = w[(u + io) % W];
+                    ax0 = add2(ax0, one, mul2(pk(wx.x, wx.y), bc2(a.cx[io])));
+                    ax1 = add2(ax1, one, mul2(pk(wx.z, wx.w), bc2(a.cx[io])));
+                }
+                l01 = add2(az0, one, ax0);
+                l23 = add2(az1, one, ax1);
+            } else if (RECIPE == RECIPE_C) {
+                /* one accumulator, z tap then x tap, (p*c)*d2inv (fd.c:30-33) */
+                const f2 dz = bc2(a.dz2inv), dx = bc2(a.dx2inv);
+                f2 a0 = mul2(zprod(za, B, a.cz[0]), dz);
+                f2 a1 = mul2(zprod(za, B + 2, a.cz[0]), dz);
+                a0 = add2(a0, one, mul2(mul2(pk(w[u % W].x, w[u % W].y), bc2(a.cx[0])), dx));
+                a1 = add2(a1, one, mul2(mul2(pk(w[u % W].z, w[u % W].w), bc2(a.cx[0])), dx));
+                FDW_UNROLL
+                for (int io = 1; io <= ORDER; io++) {
+                    const float4 &wx = w[(u + io) % W];
+                    a0 = add2(a0, one, mul2(zprod(za, B + io, a.cz[io]), dz));
+                    a1 = add2(a1, one, mul2(zprod(za, B + io + 2, a.cz[io]), dz));
+                    a0 = add2(a0, one, mul2(mul2(pk(wx.x, wx.y), bc2(a.cx[io])), dx));
+                    a1 = add2(a1, one, mul2(mul2(pk(wx.z, wx.w), bc2(a.cx[io])), dx));
+                }
+                l01 = a0;
+                l23 = a1;
+            } else {
+                /* FAST: symmetric pairs + FMA; tolerance-checked, not bit-checked */
+                f2 s0 = mul2(pk(cc[0], cc[1]), bc2(a.cz[H] + a.cx[H]));
+                f2 s1 = mul2(pk(cc[2], cc[3]), bc2(a.cz[H] + a.cx[H]));
+                FDW_UNROLL
+                for (int d = 1; d <= H; d++) {
+                    const float4 &wa = w[(u + H - d) % W], &wb = w[(u + H + d) % W];
+                    s0 = fma2(bc2(a.cz[H + d]), add2(pk(za[4 - d], za[5 - d]), one, pk(za[4 + d], za[5 + d])), s0);
+                    s1 = fma2(bc2(a.cz[H + d]), add2(pk(za[6 - d], za[7 - d]), one, pk(za[6 + d], za[7 + d])), s1);
+                    s0 = fma2(bc2(a.cx[H + d]), add2(pk(wa.x, wa.y), one, pk(wb.x, wb.y)), s0);
+                    s1 = fma2(bc2(a.cx[H + d]), add2(pk(wa.z, wa.w), one, pk(wb.z, wb.w)), s1);
+                }
+                l01 = s0;
+                l23 = s1;
+            }
+            lap[0] = lo2(l01); lap[1] = hi2(l01); lap[2] = lo2(l23); lap[3] = hi2(l23);
+        }
+        if (ring) { /* rare: the ring of width order/2 keeps lap = 0 (quirk Q2 read as 0) */
+            const bool row_in = gi >= a.lap_i0 && gi < a.lap_i1;
+            FDW_UNROLL
+            for (int k = 0; k < 4; k++)
+                if (!row_in || j0 + k < a.lap_j0 || j0 + k >= a.lap_j1) lap[k] = 0.0f;
+        }
+        if (RECIPE == RECIPE_FAST) {
+            FDW_UNROLL
+            for (int k = 0; k < 4; k++) res[k] = ffma(vv[k], lap[k], 2.0f * cc[k] - oo[k]);
+        } else if (!PACKED) {
+            FDW_UNROLL
+            for (int k = 0; k < 4; k++) res[k] = leap(cc[k], oo[k], fmul(vv[k], lap[k]));
+        } else {
+            const f2 t01 = mul2(pk(vv[0], vv[1]), pk(lap[0], lap[1]));
+            const f2 t23 = mul2(pk(vv[2], vv[3]), pk(lap[2], lap[3]));
+            res[0] = leap(cc[0], oo[0], lo2(t01));
+            res[1] = leap(cc[1], oo[1], hi2(t01));
+            res[2] = leap(cc[2], oo[2], lo2(t23));
+            res[3] = leap(cc[3], oo[3], hi2(t23));
+        }
+
+    /* ---- source (after the update, before the sponge: both families) */
+    if (near_src && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad) {
+        const float4 s4 = add_source(a, lv.src_amp, make_float4(res[0], res[1], res[2], res[3]), gi, j0);
+        res[0] = s4.x; res[1] = s4.y; res[2] = s4.z; res[3] = s4.w;
+    }
+    /* ---- receiver back-injection */
+    if ((EPI & EPI_INJECT) && gi >= a.inj_gi0 && gi < a.inj_gi0 + a.inj_n && a.inj_j >= j0 && a.inj_j < j0 + 4) {
+        long long idx = a.dobs_base + (long long)(gi - a.inj_gi0) * a.inj_nt + lv.inj_tidx;
+        float s = (idx >= 0 && idx < a.dobs_len) ? a.dobs[idx] : 0.0f;
+        FDW_UNROLL
+        for (int k = 0; k < 4; k++)
+            if (j0 + k == a.inj_j) res[k] = fadd(res[k], s);
+    }
+    return make_float4(res[0], res[1], res[2], res[3]);
+}
+
+/* Side outputs of one row, all to global memory (aux pitch a.apitch): halo push, seismogram sample, forward
+ * history, imaging.  c4 = the newer level's centre row (sponge applied as loaded), res = the new values,
+ * f4 = the imaging operand of EPI_IMG_FIELD (the reconstructed source level at this point). */
+template <int EPI, bool TAPER>
+FDW_HD void row_outputs(const StepArgs &a, const Level &lv, const float4 c4, const float4 res, const float4 f4, const int lr,
+                        const int gi, const int j0, const float *zf, const unsigned xon)
+{
+    const long long ap = a.apitch;
+    /* ---- halo push: boundary rows go to the neighbour's ghost rows over NVLink */
+    if (EPI & EPI_PUSH) {
+        if (a.push_lo && lr < GUARD) st4(a.push_lo + (long long)lr * ap + j0, res);
+        if (a.push_hi && lr >= a.push_nloc - GUARD) st4(a.push_hi + (long long)lr * ap + j0, res);
+    }
+    /* ---- seismogram sample: the newer level after one more sponge pass */
+    if ((EPI & EPI_RECORD) && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n && a.rec_j >= j0 && a.rec_j < j0 + 4) {
+        float4 s4 = c4;
+        if (TAPER) s4 = tap4(s4, zf + 4, xon >> 4, a.tx[lr], gi < a.tz_ilim, 1);
+        a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = getk(s4, a.rec_j - j0);
+    }
+    /* ---- forward history: interior rows of the newer level (sponge factor there is 1) */
+    if ((EPI & EPI_HSTORE) && gi >= a.hist_gi0 && gi < a.hist_gi0 + a.hist_n)
+        st4(lv.hist_w + (long long)(gi - a.hist_gi0) * ap + j0, c4);
+    /* ---- imaging condition */
+    if ((EPI & EPI_IMG_HIST) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
+        float *ip = a.img + (long long)(gi - a.img_gi0) * ap + j0;
+        const float4 s4 = ld4_stream(lv.hist_r + (long long)(gi - a.hist_gi0) * ap + j0);
+        float4 im = ld4(ip);
+        im.x = fadd(im.x, fmul(s4.x, c4.x));
+        im.y = fadd(im.y, fmul(s4.y, c4.y));
+        im.z = fadd(im.z, fmul(s4.z, c4.z));
+        im.w = fadd(im.w, fmul(s4.w, c4.w));
+        st4(ip, im);
+    }
+    if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
+        float *ip = a.img + (long long)(gi - a.img_gi0) * ap + j0;
+        float4 im = ld4(ip);
+        im.x = fadd(im.x, fmul(f4.x, res.x));
+        im.y = fadd(im.y, fmul(f4.y, res.y));
+        im.z = fadd(im.z, fmul(f4.z, res.z));
+        im.w = fadd(im.w, fmul(f4.w, res.w));
+        st4(ip, im);
+    }
+}
+
+/* per-thread invariants of the sponge: z factors of the 12 columns j0-4 .. j0+7, x-factor column mask */
+FDW_HD void sponge_setup(const StepArgs &a, int j0, float (&zf)[12], unsigned &xon)
+{
+    xon = 0;
+    FDW_UNROLL
+    for (int m = 0; m < 12; m++) {
+        zf[m] = a.tz[j0 - 4 + m];
+        if (j0 - 4 + m < a.tx_jlim) xon |= 1u << m;
+    }
+}
+
+template <int ORDER, int RECIPE, bool TAPER, int EPI, bool PACKED = true>
 FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int tid, int bdim)
 {
     constexpr int H = ORDER / 2, W = ORDER + 1;
@@ -261,44 +499,46 @@ FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int 
     const bool ring = j0 < a.lap_j0 || j0 + 4 > a.lap_j1 || a.grow0 + rb < a.lap_i0 || a.grow0 + re > a.lap_i1;
     const bool near_src = lv.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
 
-    /* sponge factors of the 12 columns j0-4 .. j0+7 */
     float zf[12];
     unsigned xon = 0;
-    if (TAPER) {
-        FDW_UNROLL
-        for (int m = 0; m < 12; m++) {
-            zf[m] = a.tz[j0 - 4 + m];
-            if (j0 - 4 + m < a.tx_jlim) xon |= 1u << m;
-        }
-    }
+    if (TAPER) sponge_setup(a, j0, zf, xon);
 
-    const float *__restrict__ pc = lv.p + j0 + (long long)(rb - H) * pitch; /* row being streamed in */
-    float *__restrict__ ppc = lv.pp + j0 + (long long)rb * pitch;
-    const float *__restrict__ vc = a.vdt + j0 + (long long)rb * pitch;
+    /* ONE 64-bit row cursor per thread (the centre row of the newer level); every other address of a
+     * row is the cursor plus a launch-uniform byte delta, which costs an integer add from a uniform
+     * register instead of a second and third loop-carried pointer pair (registers are what limits the
+     * resident warps of this kernel). */
+    const long long rowb = pitch * (long long)sizeof(float);
+    const long long d_in = (long long)H * rowb;                                /* centre row -> incoming row */
+    const long long d_pp = (const char *)lv.pp - (const char *)lv.p;           /* -> older level, same point */
+    const long long d_v = (const char *)a.vdt - (const char *)lv.p;            /* -> v2*dt2 */
+    const long long d_f = (const char *)lv.img_field - (const char *)lv.p;     /* -> imaging operand (EPI_IMG_FIELD) */
+    const char *pc = (const char *)(lv.p + j0 + (long long)(rb - H) * pitch);  /* prologue: row being loaded */
 
     float4 w[W];
     FDW_UNROLL
     for (int s = 0; s < 2 * H; s++) {
-        w[s] = ld4(pc);
+        w[s] = ld4((const float *)pc);
         if (TAPER) {
             int lr = rb - H + s;
             w[s] = tap4(w[s], zf + 4, xon >> 4, a.tx[lr], a.grow0 + lr < a.tz_ilim, lv.np);
         }
-        pc += pitch;
+        pc += rowb;
     }
+    pc -= d_in; /* now the centre row of the first updated row */
 
-    /* count-down loop: the only loop-carried integers are `left` and the three row pointers */
+    /* count-down loop: the only loop-carried integers are `left` and the row cursor */
     for (int left = re - rb; left > 0; left -= W) {
         FDW_UNROLL
         for (int u = 0; u < W; u++) {
             if (u < left) {
                 const int lr = re - left + u; /* local row being updated (only rare paths use it) */
                 const int gi = a.grow0 + lr;
-                float4 wn = ld4(pc); /* row lr+H */
-                const float *ctr = pc - (long long)H * pitch;
+                const float *ctr = (const float *)pc;
+                float *ppc = (float *)(pc + d_pp);
+                float4 wn = ld4((const float *)(pc + d_in)); /* row lr+H */
                 float4 l4 = ld4(ctr - 4), r4 = ld4(ctr + 4);
                 float4 o4 = ld4(ppc);
-                float4 v4 = ld4_stream(vc);
+                const float4 v4 = ld4_stream((const float *)(pc + d_v));
                 if (TAPER) {
                     const float xf = a.tx[lr];
                     const bool zon = gi < a.tz_ilim;
@@ -308,118 +548,15 @@ FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int 
                     o4 = tap4(o4, zf + 4, xon >> 4, xf, zon, lv.no);
                 }
                 w[(u + 2 * H) % W] = wn;
-                const float4 c4 = w[(u + H) % W];
-                const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
-                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-                const float oo[4] = {o4.x, o4.y, o4.z, o4.w};
-                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-                float lap[4], res[4];
-                FDW_UNROLL
-                for (int k = 0; k < 4; k++) {
-                    if (RECIPE == RECIPE_G) {
-                        /* two accumulators, ascending io, summed last (fd-code.cu:66-72).
-                         * The reference's "0 +" first add is dropped: it can only change
-                         * the sign of an all-zero sum, which provably never reaches pp. */
-                        float az = fmul(za[4 + k - H], a.cz[0]);
-                        float ax = fmul(getk(w[(u + 0) % W], k), a.cx[0]);
-                        FDW_UNROLL
-                        for (int io = 1; io <= ORDER; io++) {
-                            az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
-                            ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
-                        }
-                        lap[k] = fadd(az, ax);
-                    } else if (RECIPE == RECIPE_C) {
-                        /* one accumulator, z tap then x tap, (p*c)*d2inv (fd.c:30-33) */
-                        float acm = fmul(fmul(za[4 + k - H], a.cz[0]), a.dz2inv);
-                        acm = fadd(acm, fmul(fmul(getk(w[(u + 0) % W], k), a.cx[0]), a.dx2inv));
-                        FDW_UNROLL
-                        for (int io = 1; io <= ORDER; io++) {
-                            acm = fadd(acm, fmul(fmul(za[4 + k - H + io], a.cz[io]), a.dz2inv));
-                            acm = fadd(acm, fmul(fmul(getk(w[(u + io) % W], k), a.cx[io]), a.dx2inv));
-                        }
-                        lap[k] = acm;
-                    } else {
-                        /* FAST: symmetric pairs + FMA; tolerance-checked, not bit-checked */
-                        float s = fmul(cc[k], a.cz[H] + a.cx[H]);
-                        FDW_UNROLL
-                        for (int d = 1; d <= H; d++) {
-                            s = ffma(a.cz[H + d], za[4 + k - d] + za[4 + k + d], s);
-                            s = ffma(a.cx[H + d], getk(w[(u + H - d) % W], k) + getk(w[(u + H + d) % W], k), s);
-                        }
-                        lap[k] = s;
-                    }
+                const float4 res = row_update<ORDER, RECIPE, EPI, PACKED>(a, lv, w, u, l4, r4, o4, v4, gi, j0, ring, near_src);
+                st4(ppc, res);
+                if (EPI) {
+                    float4 f4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n)
+                        f4 = ld4_stream((const float *)(pc + d_f));
+                    row_outputs<EPI, TAPER>(a, lv, w[(u + H) % W], res, f4, lr, gi, j0, zf, xon);
                 }
-                if (ring) { /* rare: the ring of width order/2 keeps lap = 0 (quirk Q2 read as 0) */
-                    const bool row_in = gi >= a.lap_i0 && gi < a.lap_i1;
-                    FDW_UNROLL
-                    for (int k = 0; k < 4; k++)
-                        if (!row_in || j0 + k < a.lap_j0 || j0 + k >= a.lap_j1) lap[k] = 0.0f;
-                }
-                FDW_UNROLL
-                for (int k = 0; k < 4; k++) {
-                    if (RECIPE == RECIPE_FAST)
-                        res[k] = ffma(vv[k], lap[k], 2.0f * cc[k] - oo[k]);
-                    else
-                        res[k] = leap(cc[k], oo[k], fmul(vv[k], lap[k]));
-                }
-
-                /* ---- source (after the update, before the sponge: both families) */
-                if (near_src && gi >= a.src_gi - a.src_rad && gi <= a.src_gi + a.src_rad) {
-                    const float4 s4 = add_source(a, lv.src_amp, make_float4(res[0], res[1], res[2], res[3]), gi, j0);
-                    res[0] = s4.x; res[1] = s4.y; res[2] = s4.z; res[3] = s4.w;
-                }
-                /* ---- receiver back-injection */
-                if ((EPI & EPI_INJECT) && gi >= a.inj_gi0 && gi < a.inj_gi0 + a.inj_n && a.inj_j >= j0 &&
-                    a.inj_j < j0 + 4) {
-                    long long idx = a.dobs_base + (long long)(gi - a.inj_gi0) * a.inj_nt + lv.inj_tidx;
-                    float s = (idx >= 0 && idx < a.dobs_len) ? a.dobs[idx] : 0.0f;
-                    FDW_UNROLL
-                    for (int k = 0; k < 4; k++)
-                        if (j0 + k == a.inj_j) res[k] = fadd(res[k], s);
-                }
-                st4(ppc, make_float4(res[0], res[1], res[2], res[3]));
-                /* ---- halo push: boundary rows go to the neighbour's ghost rows over NVLink */
-                if (EPI & EPI_PUSH) {
-                    if (a.push_lo && lr < GUARD)
-                        st4(a.push_lo + (long long)lr * pitch + j0, make_float4(res[0], res[1], res[2], res[3]));
-                    if (a.push_hi && lr >= a.push_nloc - GUARD)
-                        st4(a.push_hi + (long long)lr * pitch + j0, make_float4(res[0], res[1], res[2], res[3]));
-                }
-
-                /* ---- seismogram sample: the newer level after one more sponge pass */
-                if ((EPI & EPI_RECORD) && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n && a.rec_j >= j0 &&
-                    a.rec_j < j0 + 4) {
-                    float4 s4 = c4;
-                    if (TAPER) s4 = tap4(s4, zf + 4, xon >> 4, a.tx[lr], gi < a.tz_ilim, 1);
-                    a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = getk(s4, a.rec_j - j0);
-                }
-                /* ---- forward history: interior rows of the newer level (sponge factor there is 1) */
-                if ((EPI & EPI_HSTORE) && gi >= a.hist_gi0 && gi < a.hist_gi0 + a.hist_n)
-                    st4(lv.hist_w + (long long)(gi - a.hist_gi0) * pitch + j0, c4);
-                /* ---- imaging condition */
-                if ((EPI & EPI_IMG_HIST) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
-                    float *ip = a.img + (long long)(gi - a.img_gi0) * pitch + j0;
-                    const float4 s4 = ld4_stream(lv.hist_r + (long long)(gi - a.hist_gi0) * pitch + j0);
-                    float4 im = ld4(ip);
-                    im.x = fadd(im.x, fmul(s4.x, c4.x));
-                    im.y = fadd(im.y, fmul(s4.y, c4.y));
-                    im.z = fadd(im.z, fmul(s4.z, c4.z));
-                    im.w = fadd(im.w, fmul(s4.w, c4.w));
-                    st4(ip, im);
-                }
-                if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
-                    float *ip = a.img + (long long)(gi - a.img_gi0) * pitch + j0;
-                    const float4 s4 = ld4_stream(lv.img_field + (long long)lr * pitch + j0);
-                    float4 im = ld4(ip);
-                    im.x = fadd(im.x, fmul(s4.x, res[0]));
-                    im.y = fadd(im.y, fmul(s4.y, res[1]));
-                    im.z = fadd(im.z, fmul(s4.z, res[2]));
-                    im.w = fadd(im.w, fmul(s4.w, res[3]));
-                    st4(ip, im);
-                }
-                pc += pitch;
-                ppc += pitch;
-                vc += pitch;
+                pc += rowb;
             }
         }
     }
@@ -428,7 +565,7 @@ FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int 
 /* stand-alone Laplacian (config 1; kernel_lap fd-source-code.cu:110-135): the
  * exact reference sequence including the leading "0 +" adds; ring written 0.
  * Same streaming structure and the same lean loop as step_thread. */
-template <int ORDER>
+template <int ORDER, bool PACKED = true>
 FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, int bdim)
 {
     constexpr int H = ORDER / 2, W = ORDER + 1;
@@ -457,15 +594,33 @@ FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, i
                 const float4 l4 = ld4(ctr - 4), r4 = ld4(ctr + 4), c4 = w[(u + H) % W];
                 const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
                 float res[4];
-                FDW_UNROLL
-                for (int k = 0; k < 4; k++) {
-                    float az = 0.0f, ax = 0.0f;
+                if (!PACKED) {
+                    FDW_UNROLL
+                    for (int k = 0; k < 4; k++) {
+                        float az = 0.0f, ax = 0.0f;
+                        FDW_UNROLL
+                        for (int io = 0; io <= ORDER; io++) {
+                            az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
+                            ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
+                        }
+                        res[k] = fadd(az, ax);
+                    }
+                } else {
+                    /* packed pairs (0,1), (2,3); every lane runs the reference's scalar sequence,
+                     * including the leading "0 +" adds (fd-source-code.cu:121-131) */
+                    const f2 one = bc2(a.one);
+                    constexpr int B = 4 - H;
+                    f2 az0 = bc2(0.0f), az1 = bc2(0.0f), ax0 = bc2(0.0f), ax1 = bc2(0.0f);
                     FDW_UNROLL
                     for (int io = 0; io <= ORDER; io++) {
-                        az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
-                        ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
+                        const float4 &wx = w[(u + io) % W];
+                        az0 = add2(az0, one, zprod(za, B + io, a.cz[io]));
+                        az1 = add2(az1, one, zprod(za, B + io + 2, a.cz[io]));
+                        ax0 = add2(ax0, one, mul2(pk(wx.x, wx.y), bc2(a.cx[io])));
+                        ax1 = add2(ax1, one, mul2(pk(wx.z, wx.w), bc2(a.cx[io])));
                     }
-                    res[k] = fadd(az, ax);
+                    const f2 r01 = add2(az0, one, ax0), r23 = add2(az1, one, ax1);
+                    res[0] = lo2(r01); res[1] = hi2(r01); res[2] = lo2(r23); res[3] = hi2(r23);
                 }
                 if (ring) {
                     const int gi = a.grow0 + re - left + u;

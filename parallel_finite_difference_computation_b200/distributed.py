@@ -119,7 +119,8 @@ class SlabPropagator:
                 ok, why = 0, str(e)
         else:
             ok = 0
-        agree = torch.tensor([ok], dtype=torch.int32, device="cuda" if self.on_gpu else "cpu")
+        agree = torch.tensor([ok], dtype=torch.int32,
+                             device="cuda" if self.on_gpu and dist.get_backend() == "nccl" else "cpu")
         dist.all_reduce(agree, op=dist.ReduceOp.MIN)  # also the barrier: nobody pushes before every slab has zeroed its flags
         if int(agree.item()) == 0:
             self.L.fdw_peer_detach(self.h)
@@ -212,11 +213,12 @@ class SlabPropagator:
             self._peer_refresh()
             return
         if self.on_gpu:
-            self.w.sync()
+            import torch
+            self.w.sync()  # the upload ran on the library stream
+            torch.cuda.current_stream().synchronize()
         for r in dist.batch_isend_irecv(self._exchange_ops(0)):
             r.wait()
         if self.on_gpu:
-            import torch
             torch.cuda.current_stream().synchronize()
 
     # -- slab-decomposed shots of the CPU family (config 5: mod_main + rtm_main, domain-divided)
@@ -292,7 +294,12 @@ class SlabPropagator:
         ihi = self.nloc - GUARD if hi_nb else self.nloc
         if self.on_gpu:
             import torch
+            # the levels, the library's own zero / upload / download work and the halo send/recv must be
+            # ordered on ONE stream: adopt torch's current stream as the library stream (fdw_set_stream
+            # drains the previous one first), then launch the rows on it
             compute = torch.cuda.current_stream()
+            if self._compute_stream != compute.cuda_stream:
+                self.set_stream(compute.cuda_stream)
             cs = C.c_void_p(compute.cuda_stream)
         else:
             cs = None

@@ -148,6 +148,26 @@ class Wave2D:
     def launch_count(self):
         return self.L.fdw_launch_count(self.h)
 
+    def graph_replays(self):
+        return self.L.fdw_counter(self.h, _lib.COUNTER_GRAPH_REPLAYS)
+
+    def persist_launches(self):
+        return self.L.fdw_counter(self.h, _lib.COUNTER_PERSIST_LAUNCHES)
+
+    def tile_launches(self):
+        return self.L.fdw_counter(self.h, _lib.COUNTER_TILE_LAUNCHES)
+
+    def shot_phase_device(self, phase, sx, sz, gz, dobs_all=None, is_=0):
+        """one phase of a CPU-family shot left on the device (fdw_shot_begin + fdw_shot_run, asynchronous):
+        bracket with mark_begin()/mark_end() for the device time of the phase's level loop"""
+        ns, ptr = 1, None
+        if dobs_all is not None:
+            dobs_all = np.ascontiguousarray(dobs_all, np.float32)
+            ns = dobs_all.size // (self.nx * self.nt)
+            ptr = dobs_all.ctypes.data_as(C.c_void_p)
+        self._ck(self.L.fdw_shot_begin(self.h, phase, sx, sz, gz, ptr, ns, is_))
+        self._ck(self.L.fdw_shot_run(self.h))
+
     def laplacian_device(self):
         self._ck(self.L.fdw_laplacian_device(self.h))
 

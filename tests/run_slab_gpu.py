@@ -22,14 +22,26 @@ import parallel_finite_difference_computation_b200 as fdw  # noqa: E402
 from parallel_finite_difference_computation_b200 import distributed as D  # noqa: E402
 
 
-HALOS = tuple(os.environ.get("FDW_HALOS", "p2p,nccl").split(","))
+# FDW_SAME_DEVICE=1: both processes share cuda:0 (a 1-GPU box): gloo is the rendezvous (NCCL refuses two ranks
+# on one GPU), the halo exchange is still the peer-memory one -- CUDA IPC maps the other process's buffers
+# whether they live on another GPU or on the same one -- so fdw_peer_levels, the in-kernel acquire/release and the
+# CUDA-graph replay are exercised; the two processes time-slice the GPU, so a spinning acquire ends when the
+# neighbour's slice comes round (slow, correct).
+SAME = os.environ.get("FDW_SAME_DEVICE") == "1"
+HALOS = tuple(os.environ.get("FDW_HALOS", "p2p" if SAME else "p2p,nccl").split(","))
+N = int(os.environ.get("FDW_SLAB_N", "2048" if SAME else "4096"))
 
 
 def main():
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lrank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
-    n, nb, nt = 4096, 40, 40
+    if SAME:
+        lrank = 0
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(lrank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+    n, nb, nt = N, 40, 40
     nx = nz = n - 2 * nb
     rng = np.random.default_rng(7)
     ve = np.empty((n, n), np.float32)
@@ -42,6 +54,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     results = {}
+    graph_replays = None
     for halo in HALOS:
         sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, rank=rank, world=world, device=lrank, order=8,
                               fac=0.75, family=fdw.FAMILY_GPU, taper=fdw.TAPER_TOP, nt=nt, halo=halo)
@@ -57,6 +70,8 @@ def main():
         parts = [None] * world
         dist.all_gather_object(parts, (na, nb_))
         results[halo] = parts
+        if halo == "p2p":
+            graph_replays = sp.w.graph_replays()
         sp.close()
     ok = True
     if rank == 0:
@@ -73,6 +88,7 @@ def main():
                 np.array_equal(older.view(np.uint32), b.view(np.uint32))
             print("slab x%d halo=%s vs single domain bitwise: %s" % (world, halo, "OK" if good else "MISMATCH"), flush=True)
             ok = ok and good
+        print("graph replays on rank 0: %s" % graph_replays, flush=True)
     for halo in HALOS:
         ok = check_domain_divided_cpu_family(rank, world, lrank, halo) and ok
     ok = check_shot_parallel(rank, world, lrank) and ok

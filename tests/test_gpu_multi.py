@@ -1,7 +1,8 @@
-"""GPU, needs >= 2 devices (skipped otherwise): launches tests/run_slab_gpu.py under torchrun -- slab
-decomposition with the peer-memory halo exchange (boundary kernel stores into the neighbour's ghost rows
-over NVLink) and with NCCL send/recv, the domain-divided mod_main + rtm_main shot, and the shot-parallel
-chained image stack, each bit for bit against one GPU."""
+"""GPU: launches tests/run_slab_gpu.py under torchrun -- slab decomposition with the peer-memory halo exchange
+(boundary kernel stores into the neighbour's ghost rows, in-kernel acquire/release, CUDA-graph level loop), the
+domain-divided mod_main + rtm_main shot and the shot-parallel chained image stack, each bit for bit against one
+GPU.  Two flavours: two processes on ONE device (always runs: CUDA IPC maps a same-device peer just as well, gloo
+is the rendezvous) and one process per GPU with NCCL (needs >= 2 devices)."""
 import os
 import subprocess
 import sys
@@ -11,19 +12,31 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.gpu
-def test_two_gpu_slab_and_shot_partitioning_bitwise():
-    import torch
-
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs two GPUs (one process per GPU)")
+def _run(port, env_extra, expect):
+    env = dict(os.environ)
+    env.update(env_extra)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "run_slab_gpu.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "run_slab_gpu.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-4000:]
     assert "MISMATCH" not in out
-    for what in ("halo=p2p vs single domain bitwise: OK", "halo=nccl vs single domain bitwise: OK",
-                 "mod_main+rtm_main x2 halo=p2p vs one GPU bitwise: OK", "chained stack vs sequential bitwise: OK"):
+    for what in expect:
         assert what in out, out[-4000:]
+    return out
+
+
+@pytest.mark.gpu
+def test_slab_and_shot_partitioning_bitwise():
+    import torch
+
+    out = _run(29543, {"FDW_SAME_DEVICE": "1"},
+               ("halo=p2p vs single domain bitwise: OK", "mod_main+rtm_main x2 halo=p2p vs one GPU bitwise: OK",
+                "chained stack vs sequential bitwise: OK"))
+    # the CUDA-graph replay of the level loop really ran
+    line = [ln for ln in out.splitlines() if ln.startswith("graph replays on rank 0:")][0]
+    assert int(line.split(":")[1]) > 0, line
+    if torch.cuda.device_count() >= 2:  # one process per GPU over NVLink, NCCL rendezvous, both halo transports
+        _run(29541, {}, ("halo=p2p vs single domain bitwise: OK", "halo=nccl vs single domain bitwise: OK",
+                         "mod_main+rtm_main x2 halo=p2p vs one GPU bitwise: OK",
+                         "chained stack vs sequential bitwise: OK"))
