@@ -209,7 +209,23 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+REFERENCE_ARM = {
+    "what": "the reference's own CPU implementation of this path (fd_step + point source + taper_apply2 = the time "
+            "loop of rtm_main.cpp:166-176, from oracle/_ref/libref_cpufam.so), serial as shipped",
+    "sample": "each step = 2 time levels of a 2048 x 2048 sub-grid of the workload (bounded so that the run ends "
+              "in minutes); throughput in the same unit",
+    "recipe": "C (fd.c:24-46: the only arithmetic the reference's CPU path has); the GPU arm runs recipe G "
+              "(kernel_lap + kernel_time, fd-code.cu:53-92) -- the same 2-D order-8 update, different rounding",
+}
+
+
 def workload_config(ngpus):
+    cfg = _workload_config(ngpus)
+    cfg["reference_arm"] = REFERENCE_ARM
+    return cfg
+
+
+def _workload_config(ngpus):
     if STRONG:
         return {"workload": "synthetic 2D stencil propagator, %dx%d extended grid in total, cut into %d slab%s along x, "
                             "order 8, recipe %s, top sponge, point source; %d time levels per step"
@@ -358,9 +374,41 @@ def run_ours(args):
     e2e_value = pts_per_step * e2e_steps / e2e_s / 1e9
     field_bytes = nloc * nze * 4
 
+    # ---- the other BASELINE configs, device-timed, in the same line (outside the headline's timed regions)
+    configs, parity = {}, None
+    for pr in props[1:]:
+        pr.close()
+    if not args.no_configs:
+        import bench_configs as BC
+
+        def guarded(name, fn):
+            try:
+                configs[name] = fn()
+            except Exception as e:  # a failing side config must not take the headline with it
+                configs[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+        if world == 1:
+            guarded("C1", lambda: BC.c1_laplacian(prop.w))
+        prop.close()
+        if world == 1:
+            guarded("C2", lambda: BC.c2_small_models(local_rank))
+        guarded("C4", lambda: BC.c4_rtm_shots(local_rank, rank, world))
+        if world == 1:
+            guarded("C5", lambda: BC.c5_cpu_family(local_rank))
+            guarded("gpu_reference", lambda: BC.gpu_reference(device=local_rank))
+        else:
+            guarded("C5", lambda: BC.c5_domain_divided(local_rank, rank, world))
+            try:
+                parity = BC.parity_n_vs_1(rank, world, local_rank, HALO)
+            except Exception as e:
+                parity = {"result": "error", "error": str(e)[:300]}
+    else:
+        prop.close()
+
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -369,13 +417,10 @@ def run_ours(args):
     per_launch_ms = ms / (args.steps * LEVELS)
     launch_bytes = float(nloc) * nze * BYTES_PER_POINT  # rank 0's slab (= NGRID rows in the weak-scaling default)
     achieved = launch_bytes / (per_launch_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("step_kernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = None, "not measured (--no-traffic)"
+    if not args.no_traffic and NGRID == 16384:
+        import bench_configs as BC
+        traffic, traffic_src = BC.measure_traffic()
 
     # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only)
     cpu = None
@@ -402,14 +447,19 @@ def run_ours(args):
                     "transfers overlap the other's levels)" if pipelined else "one step at a time")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "k_step<8,%s> fused Laplacian+leapfrog+sponge+source" % RECIPE,
                      "algorithmic_bytes_per_launch": launch_bytes, "avg_launch_ms": per_launch_ms},
         "cpu_baseline": cpu,
+        "configs": configs,
     }
+    if world > 1:
+        line["parity_n_vs_1"] = parity["result"] if parity else None
+        line["parity_n_vs_1_detail"] = parity
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -420,6 +470,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline only (skip the C1/C2/C4/C5 sub-records)")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu DRAM-byte measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

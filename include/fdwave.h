@@ -158,6 +158,22 @@ int fdw_model_shot(fdw_ctx *ctx, int sx, int sz, int gz, float *data);
  * trace), imloc [nx][nz].  Needs params.history = 1. */
 int fdw_rtm_shot_cpu(fdw_ctx *ctx, int sx, int sz, int gz, const float *dobs_all, int ns, int is,
                      float *imloc);
+/* ---- shot loop without host round trips (the reference's main() loop, fd-code.cu:480-529, re-staged for a GPU
+ * that should never wait for the host): the next shot's velocity is uploaded and premultiplied on a copy stream
+ * into a second buffer while the current shot runs; the shot image stays on the device and is stacked there in
+ * call order (img += imloc, fd-code.cu:522-528 -- the same single float add per point, so the stack equals the
+ * reference's sequential one bit for bit); one download at the end.  All calls are asynchronous; host arrays
+ * should be pinned (pageable memory works but serialises). */
+int fdw_v2_stage(fdw_ctx *ctx, const float *v2);  /* whole extended grid [nxe][nze]; must stay valid until commit */
+int fdw_v2_commit(fdw_ctx *ctx);                  /* the staged velocity becomes the current one (stream-ordered) */
+/* fd_back (fd-code.cu:290-341) on the levels fdw_forward left on the device; the shot image stays on the device */
+int fdw_backward_device(fdw_ctx *ctx, const float *dobs, int gz);
+int fdw_stack_zero(fdw_ctx *ctx);
+int fdw_stack_add(fdw_ctx *ctx);                  /* stack += image of the last fdw_backward_device */
+int fdw_stack_download(fdw_ctx *ctx, float *img); /* [nx][nz]; synchronous */
+/* device address / row pitch (floats) / rows of the stack, for reductions straight from device memory (NCCL) */
+int fdw_stack_devptr(fdw_ctx *ctx, void **ptr, long long *pitch, int *rows);
+
 /* the stencil program (fd-source-code.cu:277-352): one Laplacian sweep of an
  * [nxe][nze] host array, ring of width order/2 = 0. */
 int fdw_stencil(int order, int nxe, int nze, float dx, float dz, const float *in, float *out, int device);

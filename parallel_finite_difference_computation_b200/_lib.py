@@ -116,6 +116,13 @@ SIGNATURES = {
     "fdw_launch_count": (C.c_longlong, [C.c_void_p]),
     "fdw_laplacian_device": (C.c_int, [C.c_void_p]),
     "fdw_counter": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "fdw_v2_stage": (C.c_int, [C.c_void_p, f32p]),
+    "fdw_v2_commit": (C.c_int, [C.c_void_p]),
+    "fdw_backward_device": (C.c_int, [C.c_void_p, f32p, C.c_int]),
+    "fdw_stack_zero": (C.c_int, [C.c_void_p]),
+    "fdw_stack_add": (C.c_int, [C.c_void_p]),
+    "fdw_stack_download": (C.c_int, [C.c_void_p, f32p]),
+    "fdw_stack_devptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
     "fdw_shot_run": (C.c_int, [C.c_void_p]),
 }
 

@@ -32,6 +32,7 @@
 using fdw::GUARD;
 using fdw::StepArgs;
 using fdw::PersistArgs;
+using fdw::TileArgs;
 
 /* ------------------------------------------------------------------ errors */
 static thread_local char g_err[512] = "";
@@ -89,6 +90,11 @@ struct fdw_ctx {
     Field f[4];
     int newest[2], older[2];
     float *vdt_base = nullptr, *vdt = nullptr;
+    float *vdt2_base = nullptr;          /* staging copy of the velocity (fdw_v2_stage / fdw_v2_commit) */
+    float *stack = nullptr;              /* device-resident image stack, layout of img */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_staged = nullptr, ev_shot_done = nullptr;
+    bool staged = false, shot_done_valid = false;
     float *tz_base = nullptr, *tz = nullptr, *tx_base = nullptr, *tx = nullptr;
     float cz[9], cx[9], dz2inv, dx2inv, dt2;
     int tx_jlim, tz_ilim, tap_jlo, tap_jhi, tap_ilo, tap_ihi;
@@ -109,9 +115,12 @@ struct fdw_ctx {
     long long small_grid_limit = 1LL << 18, fork_limit = 1LL << 20; /* in float4 columns x rows */
     float *wavelet_d = nullptr; /* device copy of the wavelet (persistent kernel) */
     unsigned *barrier_d = nullptr;
+    unsigned *tileflags_d = nullptr; /* neighbour flags of the tile kernels: FDW_TILE_FLAG_WORDS words */
     int *errflag_d = nullptr;
     int coop = 0;                      /* device supports cooperative launches */
     long long persist_limit = 1LL << 18; /* float4 columns x rows below which phases run persistently */
+    int use_tile = 1;                    /* shared-memory tile kernel for those grids (FDW_TILE=0: L2-resident persistent kernel) */
+    int smem_optin = 0;                  /* largest dynamic shared memory per CTA */
     long long persist_launches = 0;
     long long tile_launches = 0;
     int li0 = 0, nli = 0; /* interior x rows owned by this slab: global rows [li0, li0+nli) */
@@ -245,6 +254,17 @@ static const void *persist_kernel(int order, int recipe, int epi)
     case 4: return fdw_persist_kernel_o4(recipe, epi);
     case 6: return fdw_persist_kernel_o6(recipe, epi);
     case 8: return fdw_persist_kernel_o8(recipe, epi);
+    }
+    return nullptr;
+}
+
+static const void *tile_kernel(int order, int recipe, int epi)
+{
+    switch (order) {
+    case 2: return fdw_tile_kernel_o2(recipe, epi);
+    case 4: return fdw_tile_kernel_o4(recipe, epi);
+    case 6: return fdw_tile_kernel_o6(recipe, epi);
+    case 8: return fdw_tile_kernel_o8(recipe, epi);
     }
     return nullptr;
 }
@@ -501,17 +521,132 @@ static int step_pair(fdw_ctx *c, int pair, int recipe, int epi, bool sponge, boo
 }
 
 /* host copy of the per-level bookkeeping step_pair does, for n levels at once */
-static void replay_bookkeeping(fdw_ctx *c, int n, bool tap)
+static void replay_bookkeeping(fdw_ctx *c, int n, bool tap, int pair = 0)
 {
     for (int l = 0; l < n; l++) {
-        Field &nw = c->f[c->newest[0]], &ol = c->f[c->older[0]];
+        Field &nw = c->f[c->newest[pair]], &ol = c->f[c->older[pair]];
         if (tap && c->prm.family == FDW_FAMILY_GPU) { nw.pend++; ol.pend++; }
         ol.pend = 0;
         if (tap && c->prm.family == FDW_FAMILY_CPU) { ol.pend = 1; nw.pend++; }
-        int t = c->newest[0];
-        c->newest[0] = c->older[0];
-        c->older[0] = t;
+        int t = c->newest[pair];
+        c->newest[pair] = c->older[pair];
+        c->older[pair] = t;
     }
+}
+
+/* ---- shared-memory tile kernels (small grids): tile plan + launch.
+ * The grid (nc float4 columns x rows) is cut into at most one tile per SM; among the cuts that fit, the
+ * one with the least work per CTA -- own points plus the halo ring it re-reads every level -- wins. */
+enum { FDW_TILE_FLAG_WORDS = 32 * 1024 }; /* 32 words (128 B) per tile */
+struct TilePlan { int tc4, tr, ntx, nty, ch, threads; size_t smem; };
+
+static bool tile_plan(const fdw_ctx *c, int nc, int rows, int nbuf, TilePlan *best)
+{
+    long long best_cost = -1;
+    for (int ntx = 1; ntx <= nc && ntx <= c->nsm; ntx++) {
+        TilePlan t;
+        t.tc4 = (nc + ntx - 1) / ntx;
+        t.ntx = (nc + t.tc4 - 1) / t.tc4;
+        int nty = c->nsm / t.ntx;
+        if (nty < 1) break;
+        if (nty > rows) nty = rows;
+        t.tr = (rows + nty - 1) / nty;
+        if (t.tr < GUARD) t.tr = GUARD < rows ? GUARD : rows; /* a tile at least as tall as the halo it feeds */
+        t.nty = (rows + t.tr - 1) / t.tr;
+        if ((long long)t.ntx * t.nty > c->nsm) continue;
+        t.ch = (t.tc4 * t.tr + 511) / 512;
+        t.threads = ((t.tc4 * ((t.tr + t.ch - 1) / t.ch) + 31) / 32) * 32;
+        if (t.threads > 512) continue;
+        t.smem = ((size_t)nbuf * (t.tr + 2 * GUARD) * 4 * (t.tc4 + 2)        /* field / velocity tiles */
+                  + 4 * (t.tc4 + 2) + 8 + t.tr + 2 * GUARD + 8) * sizeof(float); /* sponge tables */
+        if (t.smem > (size_t)c->smem_optin) continue;
+        const long long cost = (long long)t.tc4 * t.tr + 2LL * GUARD * t.tc4 + 2LL * t.tr;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; *best = t; }
+    }
+    return best_cost >= 0;
+}
+
+static int tile_launch(fdw_ctx *c, const void *k, TileArgs &ta, const TilePlan &tp)
+{
+    ta.tc4 = tp.tc4; ta.tr = tp.tr; ta.ntx = tp.ntx; ta.nty = tp.nty; ta.ch = tp.ch;
+    if (const char *e = getenv("FDW_TILE_DBG")) ta.dbg = atoi(e);
+    if (getenv("FDW_TILE_VERBOSE"))
+        fprintf(stderr, "fdwave tile plan: %d x %d tiles of %d float4 columns x %d rows, %d rows/thread, %d threads, %zu B smem\n",
+                tp.ntx, tp.nty, tp.tc4, tp.tr, tp.ch, tp.threads, tp.smem);
+    ta.pa.base.apitch = c->pitch;
+    ta.pa.base.pitch = 4LL * (tp.tc4 + 2);
+    if (tp.smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    if (tp.ntx * tp.nty * 32 > FDW_TILE_FLAG_WORDS) return 0;
+    if (cudaMemsetAsync(c->barrier_d, 0, sizeof(unsigned), c->stream) != cudaSuccess) return 0;
+    if (cudaMemsetAsync(c->tileflags_d, 0, (size_t)tp.ntx * tp.nty * 32 * sizeof(unsigned), c->stream) != cudaSuccess) return 0;
+    ta.flags = c->tileflags_d;
+    void *params[] = {&ta};
+    cudaError_t e = cudaLaunchCooperativeKernel(k, dim3(tp.ntx * tp.nty), dim3(tp.threads), params, tp.smem, c->stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError(); /* not co-resident: the caller falls back */
+        return 0;
+    }
+    c->launches++;
+    c->tile_launches++;
+    c->persist_launches++; /* same device-side error flag protocol */
+    return 1;
+}
+
+/* fill the PersistArgs part shared by the persistent and the tile kernels */
+template <class Fill>
+static void persist_args(fdw_ctx *c, int pair, StepArgs &base, bool tap, bool source, int it0, int n, int tidx_cpu,
+                         Fill fill, PersistArgs *pa)
+{
+    memset(pa, 0, sizeof *pa);
+    base.taper_on = 1; /* the sponge instantiation serves every CTA; counts of 0 make it a no-op */
+    if (source) { set_source_args(c, &base, it0); base.src_on = 1; }
+    fill(base);
+    pa->base = base;
+    pa->bufN = c->f[c->newest[pair]].r0; pa->bufO = c->f[c->older[pair]].r0;
+    pa->pendN = c->f[c->newest[pair]].pend; pa->pendO = c->f[c->older[pair]].pend;
+    pa->nlevels = n; pa->it0 = it0; pa->nt = c->prm.nt;
+    pa->sponge = tap ? 1 : 0;
+    pa->sponge_first = c->prm.family == FDW_FAMILY_GPU ? 1 : 0;
+    pa->source = source ? 1 : 0;
+    pa->tidx_cpu = tidx_cpu;
+    pa->wavelet = c->wavelet_d;
+    pa->hist = c->hist;
+    pa->hist_slice = (long long)(c->nli > 0 ? c->nli : 1) * c->pitch;
+    pa->barrier = c->barrier_d;
+    pa->error_flag = c->errflag_d;
+}
+
+static bool small_whole_grid(const fdw_ctx *c, const StepArgs &base)
+{
+    const int rows = base.row1 - base.row0, nc = base.ncol4;
+    return c->coop && c->gx0 == 0 && c->nloc == c->nxe && !c->step_open && rows > 0 && nc > 0 &&
+           (long long)nc * rows < c->persist_limit;
+}
+
+/* n consecutive levels of pair 0 by the tile kernel; 1 = done, 0 = fall back */
+template <class Fill>
+static int try_tile(fdw_ctx *c, int recipe, int epi, bool sponge, bool source, int it0, int n, int tidx_cpu, Fill fill)
+{
+    if (!c->use_tile || n < 2) return 0;
+    const void *k = tile_kernel(c->prm.order, recipe, epi);
+    if (!k) return 0;
+    StepArgs base;
+    base_args(c, 0, &base);
+    if (!small_whole_grid(c, base)) return 0;
+    if (source && (it0 < 0 || (size_t)(it0 + n) > c->wavelet.size() || !c->wavelet_d)) return 0;
+    TilePlan tp;
+    if (!tile_plan(c, base.ncol4, base.row1 - base.row0, 3, &tp)) return 0;
+    const bool tap = sponge && c->prm.taper != FDW_TAPER_NONE;
+    TileArgs ta;
+    memset(&ta, 0, sizeof ta);
+    persist_args(c, 0, base, tap, source, it0, n, tidx_cpu, fill, &ta.pa);
+    if (!tile_launch(c, k, ta, tp)) return 0;
+    replay_bookkeeping(c, n, tap);
+    return 1;
 }
 
 /* Try to run n consecutive levels of pair 0 in ONE cooperative launch (small, launch-bound
@@ -579,6 +714,7 @@ static int run_levels(fdw_ctx *c, int recipe, int epi, bool sponge, bool source,
                       FillStatic fill_static, FillLevel fill_level)
 {
     int rc;
+    if (try_tile(c, recipe, epi, sponge, source, it0, n, tidx_cpu, fill_static)) return FDW_OK;
     if (try_persistent(c, recipe, epi, sponge, source, it0, n, tidx_cpu, fill_static, &rc)) return rc;
     for (int it = it0; it < it0 + n; it++)
         CHECK(step_pair(c, 0, recipe, epi, sponge, source, it, [&](StepArgs &a) { fill_level(a, it); }));
@@ -744,6 +880,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_SMALL_GRID_LIMIT")) c->small_grid_limit = atoll(e);
     if (const char *e = getenv("FDW_PERSIST_LIMIT")) c->persist_limit = atoll(e);
     cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, prm->device);
+    if (const char *e = getenv("FDW_TILE")) c->use_tile = atoi(e);
+    cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
     if (const char *e = getenv("FDW_FUSE_FLAGS")) c->fuse_flags = atoi(e);
@@ -822,6 +960,7 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
         TRY(cudaMalloc(&c->hist, (size_t)prm->nt * img_elems * sizeof(float)));
     }
     TRY(cudaMalloc(&c->barrier_d, sizeof(unsigned)));
+    TRY(cudaMalloc(&c->tileflags_d, FDW_TILE_FLAG_WORDS * sizeof(unsigned)));
     TRY(cudaMalloc(&c->flags_d, 2 * sizeof(unsigned)));
     TRY(cudaMemsetAsync(c->flags_d, 0, 2 * sizeof(unsigned), c->stream));
     TRY(cudaMalloc(&c->pcount_d, sizeof(unsigned)));
@@ -846,8 +985,12 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     cudaFree(c->pcount_d);
     for (int k = 0; k < 4; k++) cudaFree(c->f[k].base);
     cudaFree(c->vdt_base); cudaFree(c->tz_base); cudaFree(c->tx_base);
+    cudaFree(c->vdt2_base); cudaFree(c->stack);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_staged) cudaEventDestroy(c->ev_staged);
+    if (c->ev_shot_done) cudaEventDestroy(c->ev_shot_done);
     cudaFree(c->hist); cudaFree(c->img); cudaFree(c->dobs_d); cudaFree(c->rec_d);
-    cudaFree(c->wavelet_d); cudaFree(c->barrier_d); cudaFree(c->errflag_d);
+    cudaFree(c->wavelet_d); cudaFree(c->barrier_d); cudaFree(c->errflag_d); cudaFree(c->tileflags_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1007,9 +1150,24 @@ static int image_download(fdw_ctx *c, float *imloc)
     return check_device_flag(c);
 }
 
+static int backward_core(fdw_ctx *c, const float *P, const float *PP, const float *dobs, int gz, float *imloc);
+static void graph_drop_if_any(fdw_ctx *c); /* recorded launches hold the old velocity pointer */
+
 extern "C" int fdw_backward(fdw_ctx *c, const float *P, const float *PP, const float *dobs, int gz, float *imloc)
 {
     if (!c || !dobs || !imloc || ((P == nullptr) != (PP == nullptr))) return FDW_ERR_ARG;
+    return backward_core(c, P, PP, dobs, gz, imloc);
+}
+
+extern "C" int fdw_backward_device(fdw_ctx *c, const float *dobs, int gz)
+{
+    if (!c || !dobs) return FDW_ERR_ARG;
+    return backward_core(c, nullptr, nullptr, dobs, gz, nullptr);
+}
+
+/* imloc == nullptr: leave the shot image on the device (no download, no synchronisation) */
+static int backward_core(fdw_ctx *c, const float *P, const float *PP, const float *dobs, int gz, float *imloc)
+{
     const fdw_params &p = c->prm;
     const int nt = p.nt;
     if (nt < 1) { fdw_set_error("fdw_backward: params.nt not set"); return FDW_ERR_STATE; }
@@ -1029,6 +1187,32 @@ extern "C" int fdw_backward(fdw_ctx *c, const float *P, const float *PP, const f
     CHECK(ensure_buffer(&c->dobs_d, &c->dobs_cap, ntr));
     CU(cudaMemcpyAsync(c->dobs_d, dobs, ntr * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     const int nrec = p.compat_extents ? (p.nx < c->upd_i1 ? p.nx : c->upd_i1) : p.nx;
+    auto fill_back = [&](StepArgs &a) {
+        a.dobs = c->dobs_d; a.dobs_base = 0; a.dobs_len = (long long)ntr;
+        a.inj_gi0 = p.nxb; a.inj_n = nrec; a.inj_j = gz; a.inj_nt = nt;
+        a.img = c->img; a.img_gi0 = p.nxb; a.img_n = nrec;
+    };
+    /* small grids: the whole backward pass -- both field pairs, injection, imaging -- in ONE launch of the
+     * shared-memory tile kernel */
+    if (c->use_tile && nt >= 2) {
+        const void *k = tile_kernel(p.order, p.recipe, -1);
+        StepArgs base;
+        base_args(c, 1, &base);
+        TilePlan tp;
+        if (k && small_whole_grid(c, base) && tile_plan(c, base.ncol4, base.row1 - base.row0, 5, &tp)) {
+            const bool tap = p.taper != FDW_TAPER_NONE;
+            TileArgs ta;
+            memset(&ta, 0, sizeof ta);
+            persist_args(c, 1, base, tap, false, 0, nt, 0, fill_back, &ta.pa);
+            ta.sav0 = c->f[s_pp].r0;
+            ta.sav1 = c->f[s_p].r0;
+            if (tile_launch(c, k, ta, tp)) {
+                replay_bookkeeping(c, nt, tap, 1);
+                c->saved_valid = false;
+                return imloc ? image_download(c, imloc) : FDW_OK;
+            }
+        }
+    }
     int cur = s_pp, prev1 = -1, prev2 = -1;
     for (int it = 0; it < nt; it++) {
         if (it == 0) {
@@ -1053,7 +1237,117 @@ extern "C" int fdw_backward(fdw_ctx *c, const float *P, const float *PP, const f
         }));
     }
     c->saved_valid = false;
-    return image_download(c, imloc);
+    return imloc ? image_download(c, imloc) : FDW_OK;
+}
+
+/* ------------------------------------------------------------------ shot loop without host round trips */
+__global__ void k_stack_add(float *stack, const float *img, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) stack[i] = __fadd_rn(stack[i], img[i]); /* img += imloc, fd-code.cu:525 */
+}
+#ifdef FDW_EMU
+static void thunk_stack_add(void **a) { k_stack_add(*(float **)a[0], *(const float **)a[1], *(long long *)a[2]); }
+#endif
+
+static int pipeline_init(fdw_ctx *c)
+{
+    if (c->copy_stream) return FDW_OK;
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_shot_done, cudaEventDisableTiming));
+    return FDW_OK;
+}
+
+extern "C" int fdw_v2_stage(fdw_ctx *c, const float *v2)
+{
+    if (!c || !v2) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    CHECK(pipeline_init(c));
+    if (!c->vdt2_base) {
+        CU(cudaMalloc(&c->vdt2_base, c->field_elems * sizeof(float)));
+        CU(cudaMemsetAsync(c->vdt2_base, 0, c->field_elems * sizeof(float), c->copy_stream));
+    }
+    /* the staging buffer was the current velocity until the last commit: wait for the work enqueued before it */
+    if (c->shot_done_valid) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_shot_done, 0));
+    float *r0 = c->vdt2_base + (size_t)(GUARD + 1) * c->pitch;
+    int lo = -GUARD, hi = c->nloc + GUARD;
+    if (c->gx0 + lo < 0) lo = -c->gx0;
+    if (c->gx0 + hi > c->nxe) hi = c->nxe - c->gx0;
+    CU(cudaMemcpy2DAsync(r0 + (long long)lo * c->pitch, c->pitch * sizeof(float), v2 + (size_t)(c->gx0 + lo) * c->nze,
+                         (size_t)c->nze * sizeof(float), (size_t)c->nze * sizeof(float), hi - lo, cudaMemcpyHostToDevice,
+                         c->copy_stream));
+    long long n = (long long)c->field_elems;
+    void *params[] = {&c->vdt2_base, &n, &c->dt2};
+    CU(cudaLaunchKernel(FDW_KPTR(k_scale_rows, thunk_scale_rows), dim3((unsigned)((n + 255) / 256)), dim3(256), params, 0,
+                        c->copy_stream));
+    c->launches++;
+    CU(cudaEventRecord(c->ev_staged, c->copy_stream));
+    c->staged = true;
+    return FDW_OK;
+}
+
+extern "C" int fdw_v2_commit(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    if (!c->staged) { fdw_set_error("fdw_v2_commit: nothing staged"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    /* everything enqueued so far used the old velocity: the next stage may overwrite it only after that */
+    CU(cudaEventRecord(c->ev_shot_done, c->stream));
+    c->shot_done_valid = true;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_staged, 0));
+    float *t = c->vdt_base;
+    c->vdt_base = c->vdt2_base;
+    c->vdt2_base = t;
+    c->vdt = c->vdt_base + (size_t)(GUARD + 1) * c->pitch;
+    c->staged = false;
+    graph_drop_if_any(c);
+    return FDW_OK;
+}
+
+static size_t stack_elems(const fdw_ctx *c) { return (size_t)(c->nli > 0 ? c->nli : 1) * c->pitch; }
+
+extern "C" int fdw_stack_zero(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    CHECK(bind(c));
+    if (!c->stack) CU(cudaMalloc(&c->stack, stack_elems(c) * sizeof(float)));
+    CU(cudaMemsetAsync(c->stack, 0, stack_elems(c) * sizeof(float), c->stream));
+    return FDW_OK;
+}
+
+extern "C" int fdw_stack_add(fdw_ctx *c)
+{
+    if (!c) return FDW_ERR_ARG;
+    if (!c->stack) { fdw_set_error("fdw_stack_add: call fdw_stack_zero first"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    long long n = (long long)stack_elems(c);
+    const float *img = c->img;
+    void *params[] = {&c->stack, &img, &n};
+    CU(cudaLaunchKernel(FDW_KPTR(k_stack_add, thunk_stack_add), dim3((unsigned)((n + 255) / 256)), dim3(256), params, 0, c->stream));
+    c->launches++;
+    return FDW_OK;
+}
+
+extern "C" int fdw_stack_download(fdw_ctx *c, float *img)
+{
+    if (!c || !img) return FDW_ERR_ARG;
+    if (!c->stack) { fdw_set_error("fdw_stack_download: no stack"); return FDW_ERR_STATE; }
+    CHECK(bind(c));
+    const fdw_params &p = c->prm;
+    if (c->nli > 0)
+        CU(cudaMemcpy2DAsync(img, (size_t)p.nz * sizeof(float), c->stack + p.nzb, c->pitch * sizeof(float),
+                             (size_t)p.nz * sizeof(float), c->nli, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return check_device_flag(c);
+}
+
+extern "C" int fdw_stack_devptr(fdw_ctx *c, void **ptr, long long *pitch, int *rows)
+{
+    if (!c || !ptr || !pitch || !rows) return FDW_ERR_ARG;
+    if (!c->stack) { fdw_set_error("fdw_stack_devptr: no stack"); return FDW_ERR_STATE; }
+    *ptr = c->stack; *pitch = c->pitch; *rows = c->nli > 0 ? c->nli : 1;
+    return FDW_OK;
 }
 
 /* ---- the three CPU-family shot phases, shared by the one-call pipelines below and by the
@@ -1559,6 +1853,8 @@ static void graph_drop(fdw_ctx *c)
     c->lexec = nullptr; c->lgraph = nullptr;
     c->lnodes.clear(); c->lshape.clear();
 }
+
+static void graph_drop_if_any(fdw_ctx *c) { if (c->lexec) graph_drop(c); }
 
 static void node_params(RecLaunch &r, cudaKernelNodeParams *kp, void **slots)
 {

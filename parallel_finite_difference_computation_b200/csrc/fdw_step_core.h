@@ -31,10 +31,12 @@
 
 #ifdef __CUDACC__
 #define FDW_HD __host__ __device__ __forceinline__
+#define FDW_HDM __host__ __device__ __forceinline__ /* for static member functions */
 #define FDW_UNROLL _Pragma("unroll")
 #else
 #include <math.h>
 #define FDW_HD static inline
+#define FDW_HDM inline
 #define FDW_UNROLL
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
@@ -113,6 +115,10 @@ struct StepArgs {
 struct Level {
     const float *p;
     float *pp;
+    const float *vdt; /* fl32(v2*dt2) in the layout of p / pp */
+    float *mirror;    /* tile kernel: the global copy of the level being written (null otherwise) */
+    unsigned s_p, s_pp, s_vdt, s_field; /* tile kernel: shared-window byte addresses of the tile copies' origins */
+    const float *tz, *tx; /* sponge tables (StepArgs::tz / tx, or the tile kernel's shared-memory copies) */
     int np, no;
     int src_on;
     float src_amp;
@@ -125,7 +131,7 @@ struct Level {
 FDW_HD Level level_of(const StepArgs &a)
 {
     Level lv;
-    lv.p = a.p; lv.pp = a.pp; lv.np = a.np; lv.no = a.no; lv.src_on = a.src_on; lv.src_amp = a.src_amp;
+    lv.p = a.p; lv.pp = a.pp; lv.vdt = a.vdt; lv.mirror = nullptr; lv.s_p = lv.s_pp = lv.s_vdt = lv.s_field = 0; lv.tz = a.tz; lv.tx = a.tx; lv.np = a.np; lv.no = a.no; lv.src_on = a.src_on; lv.src_amp = a.src_amp;
     lv.rec_it = a.rec_it; lv.inj_tidx = a.inj_tidx; lv.hist_w = a.hist_w; lv.hist_r = a.hist_r;
     lv.img_field = a.img_field;
     return lv;
@@ -156,6 +162,10 @@ FDW_HD Level persist_level_of(const PersistArgs &pa, int l)
     const int it = pa.it0 + l;
     lv.p = (l & 1) ? pa.bufO : pa.bufN;
     lv.pp = (l & 1) ? pa.bufN : pa.bufO;
+    lv.vdt = pa.base.vdt;
+    lv.mirror = nullptr;
+    lv.s_p = lv.s_pp = lv.s_vdt = lv.s_field = 0;
+    lv.tz = pa.base.tz; lv.tx = pa.base.tx;
     if (!pa.sponge) {
         lv.np = l == 0 ? pa.pendN : 0;
         lv.no = l == 0 ? pa.pendO : (l == 1 ? pa.pendN : 0);
@@ -440,7 +450,7 @@ FDW_HD void row_outputs(const StepArgs &a, const Level &lv, const float4 c4, con
     /* ---- seismogram sample: the newer level after one more sponge pass */
     if ((EPI & EPI_RECORD) && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n && a.rec_j >= j0 && a.rec_j < j0 + 4) {
         float4 s4 = c4;
-        if (TAPER) s4 = tap4(s4, zf + 4, xon >> 4, a.tx[lr], gi < a.tz_ilim, 1);
+        if (TAPER) s4 = tap4(s4, zf + 4, xon >> 4, lv.tx[lr], gi < a.tz_ilim, 1);
         a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = getk(s4, a.rec_j - j0);
     }
     /* ---- forward history: interior rows of the newer level (sponge factor there is 1) */
@@ -469,27 +479,57 @@ FDW_HD void row_outputs(const StepArgs &a, const Level &lv, const float4 c4, con
 }
 
 /* per-thread invariants of the sponge: z factors of the 12 columns j0-4 .. j0+7, x-factor column mask */
-FDW_HD void sponge_setup(const StepArgs &a, int j0, float (&zf)[12], unsigned &xon)
+FDW_HD bool sponge_setup(const StepArgs &a, const float *tz, int j0, float (&zf)[12], unsigned &xon)
 {
     xon = 0;
+    bool zany = false; /* some z factor of these columns differs from 1 */
     FDW_UNROLL
     for (int m = 0; m < 12; m++) {
-        zf[m] = a.tz[j0 - 4 + m];
+        zf[m] = tz[j0 - 4 + m];
+        zany = zany || zf[m] != 1.0f;
         if (j0 - 4 + m < a.tx_jlim) xon |= 1u << m;
     }
+    return zany;
 }
 
-template <int ORDER, int RECIPE, bool TAPER, int EPI, bool PACKED = true>
-FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int tid, int bdim)
+/* where the two time levels and v2*dt2 live: global memory (64-bit byte addresses) or, in the tile kernel,
+ * the CTA's shared-memory window (32-bit byte addresses, LDS / STS) */
+template <bool TILE> struct Space;
+template <> struct Space<false> {
+    typedef unsigned long long addr;
+    typedef long long diff;
+    static FDW_HDM float4 ld(addr x) { return ld4((const float *)x); }
+    static FDW_HDM float4 ld_stream(addr x) { return ld4_stream((const float *)x); }
+    static FDW_HDM void st(addr x, float4 v) { st4((float *)x, v); }
+};
+#ifdef __CUDACC__
+template <> struct Space<true> {
+    typedef unsigned addr;
+    typedef int diff;
+    static __device__ __forceinline__ float4 ld(addr x)
+    {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(x));
+        return v;
+    }
+    static __device__ __forceinline__ float4 ld_stream(addr x) { return ld(x); }
+    static __device__ __forceinline__ void st(addr x, float4 v)
+    {
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(x), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+};
+#endif
+
+/* rows [rb, re) of the float4 column at j0.  TILE: the levels, v2*dt2 and the imaging operand are the
+ * shared-memory tile copies lv.s_* (pitch a.pitch = the tile's); results are stored to the tile and mirrored
+ * to the global level lv.mirror. */
+template <int ORDER, int RECIPE, bool TAPER, int EPI, bool PACKED, bool TILE>
+FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const int rb, const int re)
 {
     constexpr int H = ORDER / 2, W = ORDER + 1;
-    const int q = a.col4_0 + bx * bdim + tid;
-    if (q >= a.ncol4) return;
-    const int j0 = q * 4;
-    const int rb = a.row0 + by * a.rows_per_cta;
-    const int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
-    if (rb >= re) return;
-    const long long pitch = a.pitch;
+    typedef Space<TILE> S;
+    typedef typename S::addr addr;
+    typedef typename S::diff diff;
 
     /* Per-thread invariants are folded into two rarely-true flags so that the streaming loop of
      * the ~99.9 % of threads that sit neither on the grid ring nor next to the source carries no
@@ -499,32 +539,40 @@ FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int 
     const bool ring = j0 < a.lap_j0 || j0 + 4 > a.lap_j1 || a.grow0 + rb < a.lap_i0 || a.grow0 + re > a.lap_i1;
     const bool near_src = lv.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
 
+    /* sponge on load.  A factor of exactly 1.0f changes nothing, so a thread whose 12 columns have no z
+     * factor skips the multiplications of every row whose x factor is 1 as well: away from the sponge the
+     * sponge instantiation then costs what the plain one does (it serves whole small grids). */
     float zf[12];
     unsigned xon = 0;
-    if (TAPER) sponge_setup(a, j0, zf, xon);
+    bool zany = false;
+    if (TAPER) zany = sponge_setup(a, lv.tz, j0, zf, xon);
 
-    /* ONE 64-bit row cursor per thread (the centre row of the newer level); every other address of a
-     * row is the cursor plus a launch-uniform byte delta, which costs an integer add from a uniform
-     * register instead of a second and third loop-carried pointer pair (registers are what limits the
-     * resident warps of this kernel). */
-    const long long rowb = pitch * (long long)sizeof(float);
-    const long long d_in = (long long)H * rowb;                                /* centre row -> incoming row */
-    const long long d_pp = (const char *)lv.pp - (const char *)lv.p;           /* -> older level, same point */
-    const long long d_v = (const char *)a.vdt - (const char *)lv.p;            /* -> v2*dt2 */
-    const long long d_f = (const char *)lv.img_field - (const char *)lv.p;     /* -> imaging operand (EPI_IMG_FIELD) */
-    const char *pc = (const char *)(lv.p + j0 + (long long)(rb - H) * pitch);  /* prologue: row being loaded */
+    /* ONE row cursor per thread (the centre row of the newer level); every other address of a row is the
+     * cursor plus a launch-uniform byte delta, which costs an integer add from a uniform register instead
+     * of a second and third loop-carried pointer pair (registers are what limits the resident warps). */
+    addr org_p, org_pp, org_v, org_f;
+    if (TILE) { org_p = (addr)lv.s_p; org_pp = (addr)lv.s_pp; org_v = (addr)lv.s_vdt; org_f = (addr)lv.s_field; }
+    else { org_p = (addr)(size_t)lv.p; org_pp = (addr)(size_t)lv.pp; org_v = (addr)(size_t)lv.vdt; org_f = (addr)(size_t)lv.img_field; }
+    const diff rowb = (diff)(a.pitch * (long long)sizeof(float));
+    const diff d_in = (diff)H * rowb;           /* centre row -> incoming row */
+    const diff d_pp = (diff)(org_pp - org_p);   /* -> older level, same point */
+    const diff d_v = (diff)(org_v - org_p);     /* -> v2*dt2 */
+    const diff d_f = (diff)(org_f - org_p);     /* -> imaging operand (EPI_IMG_FIELD) */
+    addr pc = org_p + (addr)((diff)(j0 * (int)sizeof(float)) + (diff)(rb - H) * rowb); /* prologue: row being loaded */
 
     float4 w[W];
     FDW_UNROLL
     for (int s = 0; s < 2 * H; s++) {
-        w[s] = ld4((const float *)pc);
-        if (TAPER) {
-            int lr = rb - H + s;
-            w[s] = tap4(w[s], zf + 4, xon >> 4, a.tx[lr], a.grow0 + lr < a.tz_ilim, lv.np);
+        w[s] = S::ld(pc);
+        if (TAPER && lv.np) {
+            const int lr = rb - H + s;
+            const float xf = lv.tx[lr];
+            const bool zon = a.grow0 + lr < a.tz_ilim;
+            if ((zany && zon) || (xon && xf != 1.0f)) w[s] = tap4(w[s], zf + 4, xon >> 4, xf, zon, lv.np);
         }
-        pc += rowb;
+        pc += (addr)rowb;
     }
-    pc -= d_in; /* now the centre row of the first updated row */
+    pc -= (addr)d_in; /* now the centre row of the first updated row */
 
     /* count-down loop: the only loop-carried integers are `left` and the row cursor */
     for (int left = re - rb; left > 0; left -= W) {
@@ -533,34 +581,60 @@ FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int 
             if (u < left) {
                 const int lr = re - left + u; /* local row being updated (only rare paths use it) */
                 const int gi = a.grow0 + lr;
-                const float *ctr = (const float *)pc;
-                float *ppc = (float *)(pc + d_pp);
-                float4 wn = ld4((const float *)(pc + d_in)); /* row lr+H */
-                float4 l4 = ld4(ctr - 4), r4 = ld4(ctr + 4);
-                float4 o4 = ld4(ppc);
-                const float4 v4 = ld4_stream((const float *)(pc + d_v));
+                const addr ppc = pc + (addr)d_pp;
+                float4 wn = S::ld(pc + (addr)d_in); /* row lr+H */
+                float4 l4 = S::ld(pc - 16), r4 = S::ld(pc + 16);
+                float4 o4 = S::ld(ppc);
+                const float4 v4 = S::ld_stream(pc + (addr)d_v);
                 if (TAPER) {
-                    const float xf = a.tx[lr];
-                    const bool zon = gi < a.tz_ilim;
-                    wn = tap4(wn, zf + 4, xon >> 4, a.tx[lr + H], gi + H < a.tz_ilim, lv.np);
-                    l4 = tap4(l4, zf, xon, xf, zon, lv.np);
-                    r4 = tap4(r4, zf + 8, xon >> 8, xf, zon, lv.np);
-                    o4 = tap4(o4, zf + 4, xon >> 4, xf, zon, lv.no);
+                    const float xf = lv.tx[lr], xfn = lv.tx[lr + H];
+                    const bool zon = gi < a.tz_ilim, zonn = gi + H < a.tz_ilim;
+                    if ((zany && zonn) || (xon && xfn != 1.0f)) wn = tap4(wn, zf + 4, xon >> 4, xfn, zonn, lv.np);
+                    if ((zany && zon) || (xon && xf != 1.0f)) {
+                        l4 = tap4(l4, zf, xon, xf, zon, lv.np);
+                        r4 = tap4(r4, zf + 8, xon >> 8, xf, zon, lv.np);
+                        o4 = tap4(o4, zf + 4, xon >> 4, xf, zon, lv.no);
+                    }
                 }
                 w[(u + 2 * H) % W] = wn;
                 const float4 res = row_update<ORDER, RECIPE, EPI, PACKED>(a, lv, w, u, l4, r4, o4, v4, gi, j0, ring, near_src);
-                st4(ppc, res);
+                S::st(ppc, res);
+                if (TILE) st4(lv.mirror + (long long)lr * a.apitch + j0, res);
                 if (EPI) {
                     float4 f4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n)
-                        f4 = ld4_stream((const float *)(pc + d_f));
+                        f4 = S::ld_stream(pc + (addr)d_f);
                     row_outputs<EPI, TAPER>(a, lv, w[(u + H) % W], res, f4, lr, gi, j0, zf, xon);
                 }
-                pc += rowb;
+                pc += (addr)rowb;
             }
         }
     }
 }
+
+template <int ORDER, int RECIPE, bool TAPER, int EPI, bool PACKED = true>
+FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int tid, int bdim)
+{
+    const int q = a.col4_0 + bx * bdim + tid;
+    if (q >= a.ncol4) return;
+    const int rb = a.row0 + by * a.rows_per_cta;
+    const int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
+    if (rb >= re) return;
+    step_rows<ORDER, RECIPE, TAPER, EPI, PACKED, false>(a, lv, q * 4, rb, re);
+}
+
+/* arguments of the shared-memory tile kernels (small grids): the grid is cut into
+ * ntx x nty tiles of tc4 float4 columns x tr rows, one CTA per tile, every tile resident in its
+ * SM's shared memory for a whole propagation phase (see fdw_tile_core.h). */
+struct TileArgs {
+    PersistArgs pa;   /* pa.base.pitch = the tile's shared-memory pitch, pa.base.apitch = the global one */
+    int tc4, tr, ntx, nty;
+    int ch;           /* rows per thread */
+    /* GPU-family backward (k_tile_back): the two saved levels of the source field, u(T) and u(T-1) */
+    float *sav0, *sav1;
+    unsigned *flags; /* one "levels completed" word per tile, 128 B apart, zeroed before the launch */
+    int dbg; /* 8: device-wide counter barrier instead of neighbour flags.  Timing experiments only (FDW_TILE_DBG; results are wrong when set): 1 no barrier, 2 no update, 4 no ring load */
+};
 
 /* stand-alone Laplacian (config 1; kernel_lap fd-source-code.cu:110-135): the
  * exact reference sequence including the leading "0 +" adds; ring written 0.

@@ -405,6 +405,107 @@ def stack_images_chain(shot_images, shape):
     return t.cpu().numpy()
 
 
+class ShotPipeline:
+    """Shot-parallel RTM of the GPU family (main() loop of fd-code.cu:480-529) without host round trips: this rank
+    migrates its shots on its own GPU; the next shot's velocity is staged (pinned memory -> second device buffer,
+    premultiplied on a copy stream) while the current shot runs, the shot images are stacked on the device in shot
+    order, the cross-rank stack is reduced straight from device memory, and the image is downloaded once.
+
+    stack = "device"    single rank: sequential stack, bit-identical to the reference's img += imloc
+            "chain"     the running stack travels down the ranks in shot order (contiguous shot blocks): still
+                        bit-identical to the sequential reference order
+            "allreduce" per-rank partial stacks + one all-reduce (fast path; summation order unspecified)"""
+
+    def __init__(self, nx, nz, nxb, nzb, dx, dz, dt, nt, device=0, order=8, fac=0.7, compat_extents=False, lib=None):
+        self.w = Wave2D(nx, nz, nxb, nzb, dx, dz, dt, order=order, fac=fac, family=_lib.FAMILY_GPU,
+                        taper=_lib.TAPER_TOP, compat_extents=compat_extents, device=device, nt=nt, lib=lib)
+        self.nx, self.nz, self.nt = nx, nz, nt
+        self._pinned = []
+
+    def close(self):
+        self.w.close()
+
+    def set_wavelet(self, s):
+        self.w.set_wavelet(s)
+
+    def pinned(self, shape):
+        """page-locked float32 host array (torch owns the allocation; kept alive by the pipeline)"""
+        import torch
+        t = torch.zeros(shape, dtype=torch.float32).pin_memory()
+        self._pinned.append(t)
+        return t.numpy()
+
+    def _stack_tensor(self):
+        import torch
+        ptr, pitch, rows = self.w.stack_devptr()
+        return torch.as_tensor(_CudaView(ptr, pitch * rows), device="cuda")
+
+    def run_shots(self, shots, v2_of_shot, dobs_of_shot, sx_of_shot, sz, gz, stack="device"):
+        import torch.distributed as dist
+        w = self.w
+        multi = stack in ("chain", "allreduce") and dist.is_initialized() and dist.get_world_size() > 1
+        w.stack_zero()
+        if shots:
+            w.v2_stage(v2_of_shot(shots[0]))
+        nccl = multi and dist.get_backend() == "nccl"  # gloo (tests on one device): bounce through the host
+        if multi and stack == "chain" and dist.get_rank() > 0:
+            w.sync()
+            t = self._stack_tensor()  # the stack of all earlier shots arrives here
+            if nccl:
+                dist.recv(t, dist.get_rank() - 1)
+            else:
+                h = t.cpu()
+                dist.recv(h, dist.get_rank() - 1)
+                t.copy_(h)
+            import torch
+            torch.cuda.current_stream().synchronize()
+        for i, is_ in enumerate(shots):
+            w.v2_commit()
+            if i + 1 < len(shots):
+                w.v2_stage(v2_of_shot(shots[i + 1]))  # overlaps this shot
+            w.forward(sx_of_shot(is_), sz, download=False)
+            w.backward_device(dobs_of_shot(is_), gz)
+            w.stack_add()
+        if multi:
+            w.sync()
+            import torch
+            t = self._stack_tensor()
+            x = t if nccl else t.cpu()
+            if stack == "chain":
+                rank, world = dist.get_rank(), dist.get_world_size()
+                if rank < world - 1:
+                    dist.send(x, rank + 1)
+                dist.broadcast(x, world - 1)
+            else:
+                dist.all_reduce(x)
+            if not nccl:
+                t.copy_(x)
+            torch.cuda.current_stream().synchronize()
+        return w.stack_download()
+
+    def time_one_shot(self, v2, dobs, sx, sz, gz):
+        """device times (CUDA events) of the pieces of one shot"""
+        w = self.w
+        w.sync()
+        t0 = _now()
+        w.v2_stage(v2)
+        w.v2_commit()
+        w.sync()
+        stage_ms = (_now() - t0) * 1e3
+        w.mark_begin()
+        w.forward(sx, sz, download=False)
+        f_ms = w.mark_end()
+        w.mark_begin()
+        w.backward_device(dobs, gz)
+        b_ms = w.mark_end()
+        return {"v2_stage_ms_wall_unoverlapped": stage_ms, "forward_ms": f_ms, "backward_ms": b_ms}
+
+
+def _now():
+    import time
+    return time.perf_counter()
+
+
 def migrate_shots_gpu_family(wave, shots, v2_of_shot, dobs_of_shot, sx_of_shot, sz, gz, stack="chain"):
     """Shot-parallel RTM with the GPU family's algorithm (main() loop of fd-code.cu:480-529):
     this rank migrates `shots` (from shot_partition) on its own GPU -- forward with the two

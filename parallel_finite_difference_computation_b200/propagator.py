@@ -131,6 +131,42 @@ class Wave2D:
         self._ck(self.L.fdw_rtm_shot_cpu(self.h, sx, sz, gz, dobs_all.reshape(-1), ns, is_, im))
         return im
 
+    def shot_end(self, out):
+        """host result of the phase opened by shot_phase_device: traces [nx][nt] or image [nx][nz]"""
+        self._ck(self.L.fdw_shot_end(self.h, out))
+        return out
+
+    # -- shot loop without host round trips (fdw_v2_stage .. fdw_stack_download)
+    def v2_stage(self, v2):
+        """upload + premultiply the NEXT shot's squared velocity into the second buffer on the copy stream
+        (asynchronous; pass pinned memory and keep it alive until v2_commit)"""
+        self._ck(self.L.fdw_v2_stage(self.h, self._grid(v2, "v2")))
+
+    def v2_commit(self):
+        self._ck(self.L.fdw_v2_commit(self.h))
+
+    def backward_device(self, dobs, gz):
+        """fd_back on the levels forward(download=False) left on the device; the image stays there"""
+        dobs = np.ascontiguousarray(dobs, np.float32)
+        assert dobs.size == self.nx * self.nt
+        self._ck(self.L.fdw_backward_device(self.h, dobs.reshape(-1), gz))
+
+    def stack_zero(self):
+        self._ck(self.L.fdw_stack_zero(self.h))
+
+    def stack_add(self):
+        self._ck(self.L.fdw_stack_add(self.h))
+
+    def stack_download(self):
+        im = np.zeros((self.nx, self.nz), np.float32)
+        self._ck(self.L.fdw_stack_download(self.h, im))
+        return im
+
+    def stack_devptr(self):
+        ptr, pitch, rows = C.c_void_p(), C.c_longlong(), C.c_int()
+        self._ck(self.L.fdw_stack_devptr(self.h, C.byref(ptr), C.byref(pitch), C.byref(rows)))
+        return ptr.value, pitch.value, rows.value
+
     # -- benchmarks / plumbing
     def devinfo(self):
         d = _lib.DevInfo()

@@ -71,7 +71,9 @@ cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *, const void *, i
 cudaError_t cudaLaunchKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t);
 /* runs the thunk emu_levels times, level by level (the grid barrier of the real kernel) */
 cudaError_t cudaLaunchCooperativeKernel(const void *func, dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t);
-enum { cudaDevAttrCooperativeLaunch = 95 };
+enum { cudaDevAttrCooperativeLaunch = 95, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline cudaError_t cudaFuncSetAttribute(const void *, int, int) { return cudaSuccess; }
 cudaError_t cudaDeviceGetAttribute(int *value, int attr, int device);
 /* Acquire side of a flag in the host stand-in.  Default: kernels run synchronously in lock-step tests, so an
  * unmet flag is a protocol error (returns false at once).  With FDW_EMU_SPIN=1 the slabs run in separate host

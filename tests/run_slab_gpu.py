@@ -160,6 +160,18 @@ def check_shot_parallel(rank, world, lrank):
                 seq += w.backward(dobs[k], nb)
             ok = np.array_equal(img.view(np.uint32), seq.view(np.uint32))
             print("shot-parallel x%d chained stack vs sequential bitwise: %s" % (world, "OK" if ok else "MISMATCH"), flush=True)
+    # the same job through the device-resident pipeline (staged velocity, image stack on the device, chained across
+    # the ranks straight from device memory)
+    pipe = D.ShotPipeline(nx, nz, nb, nb, 10.0, 10.0, 0.001, nt=nt, device=lrank, order=8, fac=0.75, compat_extents=True)
+    pipe.set_wavelet(srce)
+    v2p = pipe.pinned((nxe, nze))
+    v2p[:] = v2
+    img2 = pipe.run_shots(shots, lambda k: v2p, lambda k: dobs[k], lambda k: nb + 10 + 20 * k, nb, nb, stack="chain")
+    pipe.close()
+    if rank == 0:
+        ok2 = np.array_equal(img2.view(np.uint32), seq.view(np.uint32))
+        print("shot pipeline x%d device stack chained vs sequential bitwise: %s" % (world, "OK" if ok2 else "MISMATCH"), flush=True)
+        ok = ok and ok2
     return ok
 
 

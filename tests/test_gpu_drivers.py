@@ -192,3 +192,31 @@ def test_reference_mains_relinked_against_our_shim(tmp_path, golden_dir):
     for f in ("dir.img", "dir.image"):
         PC.assert_bit_equal(np.fromfile(tmp_path / f, np.float32), np.fromfile(os.path.join(d, f), np.float32),
                             "relinked rtm_main " + f)
+
+
+@pytest.mark.parametrize("dims", [(101, 83, 24, 400, 2), (151, 151, 40, 300, 1)])
+def test_reference_rtm_main_relinked_against_gpufam_shim(tmp_path, dims):
+    """Function-level boundary of the GPU family: the reference's OWN main() of fd-code.cu (cut out of
+    the file at build time, oracle/Makefile target rtm_code_relinked) linked against libfdwave_gpufam.so -- i.e.
+    the reference program with its kernels, fd_init, fd_forward and fd_back replaced by this library -- must write
+    the same dir.image as our own driver bin/rtm_code bit for bit, and match the reference's CUDA program within
+    the tolerance of test_rtm_code_vs_reference_cuda_program."""
+    if not R.path("rtm_code_relinked"):
+        pytest.skip("oracle/_ref/rtm_code_relinked not built")
+    nx, nz, nb, nt, ns = dims
+    ours, relinked, ref = tmp_path / "ours", tmp_path / "relinked", tmp_path / "ref"
+    for d in (ours, relinked, ref):
+        os.makedirs(d)
+        _write_rtm_case(str(d), nx, nz, nb, nt, ns, seed=5)
+    run([os.path.join(BIN, "rtm_code"), "./input.dat"], ours)
+    run([R.path("rtm_code_relinked"), "./input.dat"], relinked)
+    a = np.fromfile(ours / "out" / "dir.image", np.float32).reshape(nx, nz)
+    b = np.fromfile(relinked / "out" / "dir.image", np.float32).reshape(nx, nz)
+    assert np.abs(a).max() > 0
+    PC.assert_bit_equal(b, a, "reference main() on libfdwave_gpufam vs bin/rtm_code dir.image")
+    assert open(ours / "image.num").read() == open(relinked / "image.num").read()
+    if R.path("rtm_code_ref"):
+        run([R.path("rtm_code_ref"), "./input.dat"], ref)
+        c = np.fromfile(ref / "out" / "dir.image", np.float32).reshape(nx, nz)
+        print("relinked vs reference CUDA program: rel-L2 %.3g" % PC.rel_l2(b, c))
+        assert PC.rel_l2(b, c) <= 5e-3

@@ -32,7 +32,7 @@ def test_slab_and_shot_partitioning_bitwise():
 
     out = _run(29543, {"FDW_SAME_DEVICE": "1"},
                ("halo=p2p vs single domain bitwise: OK", "mod_main+rtm_main x2 halo=p2p vs one GPU bitwise: OK",
-                "chained stack vs sequential bitwise: OK"))
+                "chained stack vs sequential bitwise: OK", "device stack chained vs sequential bitwise: OK"))
     # the CUDA-graph replay of the level loop really ran
     line = [ln for ln in out.splitlines() if ln.startswith("graph replays on rank 0:")][0]
     assert int(line.split(":")[1]) > 0, line

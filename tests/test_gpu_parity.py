@@ -33,11 +33,15 @@ def test_stencil_golden_output_teste(lib, golden_dir):
     PC.case_stencil_golden(lib, golden_dir)
 
 
-@pytest.fixture(params=["persistent", "one-launch", "rectangles+fork"])
+@pytest.fixture(params=["tile", "persistent", "one-launch", "rectangles+fork"])
 def launch_mode(request, monkeypatch):
-    if request.param != "persistent":
+    # tile: the default for small grids (shared-memory tiles, one cooperative launch per phase);
+    # persistent: round 1's L2-resident kernel; the others: one (or several) launches per level
+    if request.param == "persistent":
+        monkeypatch.setenv("FDW_TILE", "0")
+    if request.param not in ("persistent", "tile"):
         monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")  # one launch per level
-    if request.param not in ("one-launch", "persistent"):
+    if request.param not in ("one-launch", "persistent", "tile"):
         monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
         monkeypatch.setenv("FDW_FORK_LIMIT", "0")
     return request.param
@@ -103,6 +107,63 @@ def test_mod_main_shot(lib, launch_mode):
 @pytest.mark.parametrize("is_", [0, 1])
 def test_rtm_main_shot(lib, launch_mode, is_):
     PC.case_rtm_shot_cpu(lib, is_=is_)
+
+
+def test_tile_kernel_runs_whole_phases(lib):
+    """small grids: every phase is ONE launch of the shared-memory tile kernel (forward, the GPU family's
+    backward pass with both field pairs, mod_main and rtm_main shots), bit-exact like every other path"""
+    nx, nz, nb, nt = 150, 130, 24, 60
+    nxe, nze = nx + 2 * nb, nz + 2 * nb
+    rng = np.random.default_rng(3)
+    v2 = np.full((nxe, nze), np.float32(2500.0) ** 2, np.float32)
+    dobs = rng.standard_normal((nx, nt)).astype(np.float32)
+    with Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, order=8, fac=0.75, family=FAMILY_GPU, taper=TAPER_TOP,
+                compat_extents=True, nt=nt) as w:
+        w.set_v2(v2)
+        w.set_wavelet(fdw.host.ricker_wavelet(nt, 0.001, 20.0, FAMILY_GPU))
+        l0 = w.launch_count()
+        w.forward(nb + 10, nb, download=False)
+        assert w.tile_launches() == 1
+        w.backward(dobs, nb)
+        assert w.tile_launches() == 2
+        assert w.launch_count() - l0 <= 6  # two phases + the materialisation of the two saved levels
+    with Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, order=8, fac=0.01, family=FAMILY_CPU, taper=TAPER_TOP, nt=nt,
+                history=True) as w:
+        w.set_v2(v2)
+        w.set_wavelet(fdw.host.ricker_wavelet(nt, 0.001, 20.0, FAMILY_CPU))
+        w.rtm_shot_cpu(nb + 10, nb, nb, dobs[None], 0)
+        assert w.tile_launches() == 2
+
+
+@pytest.mark.parametrize("small", [True, False])
+def test_shot_pipeline_device_stack_equals_sequential_loop(lib, small, monkeypatch):
+    """fdw_v2_stage / commit, fdw_backward_device, fdw_stack_*: the shot loop without host round trips gives the
+    reference's sequential img += imloc bit for bit (tile kernel and per-level launches)"""
+    from parallel_finite_difference_computation_b200 import distributed as D
+    if not small:
+        monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
+    nx, nz, nb, nt, ns = 90, 70, 16, 80, 3
+    nxe, nze = nx + 2 * nb, nz + 2 * nb
+    rng = np.random.default_rng(11)
+    v2s = [np.full((nxe, nze), np.float32(2000.0 + 300.0 * k) ** 2, np.float32) for k in range(ns)]
+    dobs = rng.standard_normal((ns, nx, nt)).astype(np.float32)
+    srce = fdw.host.ricker_wavelet(nt, 0.001, 25.0, FAMILY_GPU)
+    with Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, order=8, fac=0.75, family=FAMILY_GPU, taper=TAPER_TOP, nt=nt) as w:
+        w.set_wavelet(srce)
+        seq = np.zeros((nx, nz), np.float32)
+        for k in range(ns):
+            w.set_v2(v2s[k])
+            w.forward(nb + 5 + 20 * k, nb, download=False)
+            seq += w.backward(dobs[k], nb)
+    pipe = D.ShotPipeline(nx, nz, nb, nb, 10.0, 10.0, 0.001, nt=nt, order=8, fac=0.75)
+    pipe.set_wavelet(srce)
+    pinned = [pipe.pinned((nxe, nze)) for _ in range(ns)]
+    for k in range(ns):
+        pinned[k][:] = v2s[k]
+    got = pipe.run_shots(list(range(ns)), lambda k: pinned[k], lambda k: dobs[k], lambda k: nb + 5 + 20 * k, nb, nb)
+    pipe.close()
+    PC.assert_bit_equal(got, seq, "shot pipeline image stack")
+    assert np.abs(seq).max() > 0
 
 
 # ------------------------------------------------------------------ reference golden files

@@ -28,6 +28,105 @@ __global__ void __maxnreg__(MAXR) k5lap(const __grid_constant__ StepArgs a, floa
     lap_thread<8, PACKED>(a, lap, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
 
+/* ---- round-2 trial: operands prefetched K rows ahead with cp.async (LDGSTS) into a per-warp shared-memory ring.
+ * Bytes in flight no longer occupy registers: at 32 warps/SM the register kernel keeps ~49 KB/SM in flight, the
+ * 3R+1W stream ceiling (7.2 TB/s, below) needs more.  One warp = one independent unit: lane t copies ITS float4
+ * column of the incoming p row, of pp and of v2*dt2 for row r+K while row r is computed; the centre row's left /
+ * right neighbours are read from the neighbour lanes' ring slots (lanes 0 / 31: from global, L2).  The x window
+ * stays in registers.  Arithmetic = row_update of the shipped header, i.e. bit-identical. */
+__device__ __forceinline__ void cpa_ca(const float4 *s, const float *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cpa_cg(const float4 *s, const float *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int RECIPE, bool PACKED, int K, int MAXR>
+__global__ void __maxnreg__(MAXR) k5pf(const __grid_constant__ StepArgs a)
+{
+    constexpr int H = 4, W = 9, RP = H + K;
+    extern __shared__ float4 sm4[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *sp = sm4 + warp * (RP + 2 * K) * 32; /* [slot][lane] */
+    float4 *so = sp + RP * 32, *sv = so + K * 32;
+    const int q = a.col4_0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = q < a.ncol4;
+    const int j0 = 4 * q;
+    const int rb = a.row0 + blockIdx.y * a.rows_per_cta;
+    const int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
+    if (rb >= re) return;
+    const long long pitch = a.pitch;
+    const Level lv = level_of(a);
+    const bool ring = j0 < a.lap_j0 || j0 + 4 > a.lap_j1 || a.grow0 + rb < a.lap_i0 || a.grow0 + re > a.lap_i1;
+    const bool near_src = lv.src_on && j0 + 3 >= a.src_j - a.src_rad && j0 <= a.src_j + a.src_rad;
+    const float *gp = a.p + j0;
+    float *gpp = a.pp + j0;
+    const float *gv = a.vdt + j0;
+
+    float4 w[W];
+    int sc = 0;  /* ring slot of the centre row r */
+    int so_i = 0; /* pp / vdt slot of row r */
+    /* prologue: rows rb-H..rb-1 straight into registers; rows rb..rb+H-1 through the ring (their neighbours need them) */
+    if (act) {
+#pragma unroll
+        for (int s2 = 0; s2 < H; s2++) w[s2] = ld4(gp + (long long)(rb - H + s2) * pitch);
+#pragma unroll
+        for (int s2 = 0; s2 < H; s2++) cpa_ca(&sp[s2 * 32 + lane], gp + (long long)(rb + s2) * pitch);
+    }
+    cpa_commit();
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        if (act && rb + i < re) {
+            cpa_ca(&sp[(H + i) * 32 + lane], gp + (long long)(rb + i + H) * pitch);
+            cpa_cg(&so[i * 32 + lane], gpp + (long long)(rb + i) * pitch);
+            cpa_cg(&sv[i * 32 + lane], gv + (long long)(rb + i) * pitch);
+        }
+        cpa_commit();
+    }
+    cpa_wait<K>();
+    __syncwarp();
+    if (act) {
+#pragma unroll
+        for (int s2 = 0; s2 < H; s2++) w[H + s2] = sp[s2 * 32 + lane];
+    }
+    for (int left = re - rb; left > 0; left -= W) {
+#pragma unroll
+        for (int u = 0; u < W; u++) {
+            if (u < left) {
+                const int r = re - left + u;
+                const int gi = a.grow0 + r;
+                cpa_wait<K - 1>();
+                __syncwarp();
+                int sin = sc + H; /* slot of the incoming row r+H */
+                if (sin >= RP) sin -= RP;
+                if (act) {
+                    const float4 wn = sp[sin * 32 + lane];
+                    const float4 o4 = so[so_i * 32 + lane], v4 = sv[so_i * 32 + lane];
+                    const float *ctr = gp + (long long)r * pitch;
+                    const float4 l4 = lane > 0 ? sp[sc * 32 + lane - 1] : ld4(ctr - 4);
+                    const float4 r4 = lane < 31 ? sp[sc * 32 + lane + 1] : ld4(ctr + 4);
+                    w[(u + 2 * H) % W] = wn;
+                    const float4 res = row_update<8, RECIPE, 0, PACKED>(a, lv, w, u, l4, r4, o4, v4, gi, j0, ring, near_src);
+                    st4(gpp + (long long)r * pitch, res);
+                }
+                __syncwarp(); /* every lane has read the centre row's slot before it is recycled */
+                if (act && r + K < re) {
+                    cpa_ca(&sp[sc * 32 + lane], gp + (long long)(r + K + H) * pitch);
+                    cpa_cg(&so[so_i * 32 + lane], gpp + (long long)(r + K) * pitch);
+                    cpa_cg(&sv[so_i * 32 + lane], gv + (long long)(r + K) * pitch);
+                }
+                cpa_commit();
+                if (++sc == RP) sc = 0;
+                if (++so_i == K) so_i = 0;
+            }
+        }
+    }
+}
+
 /* access-pattern ceilings: the step kernel's streams without its arithmetic, halo or x window.
  * MODE 0: 3 reads + 1 write per float4 (p, pp, vdt -> pp), MODE 1: 3 reads only, MODE 2: 1 read + 1 write (copy) */
 template <int MODE, int ILP>
@@ -191,6 +290,70 @@ int main(int argc, char **argv)
                v.packed ? "packed" : "scalar", v.maxr, fa.numRegs, fa.localSizeBytes, per, gpts,
                is_ref ? "(reference)" : (bad == 0 ? "bitwise OK" : "MISMATCH"));
         fflush(stdout);
+    }
+    /* ---- cp.async prefetch trial (recipe G plain and recipe C plain), vs ref[] of the matching recipe */
+    {
+        struct PF { const char *n; const void *fn; int recipe, k; } pf[] = {
+            {"pf G scalar K2 r64", (const void *)k5pf<0, false, 2, 64>, 0, 2}, {"pf G scalar K3 r64", (const void *)k5pf<0, false, 3, 64>, 0, 3},
+            {"pf G packed K3 r64", (const void *)k5pf<0, true, 3, 64>, 0, 3}, {"pf G scalar K3 r72", (const void *)k5pf<0, false, 3, 72>, 0, 3},
+            {"pf G scalar K4 r80", (const void *)k5pf<0, false, 4, 80>, 0, 4}, {"pf G packed K4 r80", (const void *)k5pf<0, true, 4, 80>, 0, 4},
+            {"pf C packed K3 r64", (const void *)k5pf<1, true, 3, 64>, 1, 3}, {"pf C packed K4 r80", (const void *)k5pf<1, true, 4, 80>, 1, 4}};
+        const int geo[][2] = {{32, 7}, {32, 14}, {32, 28}, {32, 64}, {64, 28}, {128, 28}};
+        std::vector<float> x(elems), y(elems);
+        int last_recipe = -1;
+        for (auto &v : pf) {
+            for (int k = 0; k <= 8; k++) { float c = (float)c8[k]; a.cz[k] = v.recipe == 1 ? c : d2 * c; a.cx[k] = a.cz[k]; }
+            if (v.recipe != last_recipe) { /* reference result of this recipe: scalar 64-register kernel, shipped geometry */
+                const void *rf = v.recipe == 0 ? (const void *)k5<0, 0, false, 64> : (const void *)k5<1, 0, false, 64>;
+                for (int k = 0; k < 2; k++) CK(cudaMemcpy(ref[k], init[k].data(), elems * 4, cudaMemcpyHostToDevice));
+                a.rows_per_cta = rpc;
+                for (int it = 0; it < reps; it++) {
+                    a.p = ref[it & 1] + (size_t)(GUARD + 1) * pitch; a.pp = ref[(it + 1) & 1] + (size_t)(GUARD + 1) * pitch;
+                    a.vdt = vdt + (size_t)(GUARD + 1) * pitch;
+                    void *params[] = {&a};
+                    CK(cudaLaunchKernel(rf, grid, block, params, 0, 0));
+                }
+                CK(cudaDeviceSynchronize());
+                last_recipe = v.recipe;
+            }
+            CK(cudaFuncSetAttribute(v.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            cudaFuncAttributes fa;
+            CK(cudaFuncGetAttributes(&fa, v.fn));
+            for (auto &gg : geo) {
+                a.rows_per_cta = gg[1];
+                dim3 b2(gg[0]), g2((a.ncol4 + gg[0] - 1) / gg[0], (nxe + gg[1] - 1) / gg[1]);
+                const size_t smem = (size_t)(gg[0] / 32) * (4 + 3 * v.k) * 32 * 16;
+                int occ = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, gg[0], smem));
+                float best = 1e30f;
+                for (int trial = 0; trial < 3; trial++) {
+                    for (int k = 0; k < 2; k++) CK(cudaMemcpy(f[k], init[k].data(), elems * 4, cudaMemcpyHostToDevice));
+                    CK(cudaDeviceSynchronize());
+                    CK(cudaEventRecord(e0));
+                    for (int it = 0; it < reps; it++) {
+                        a.p = f[it & 1] + (size_t)(GUARD + 1) * pitch; a.pp = f[(it + 1) & 1] + (size_t)(GUARD + 1) * pitch;
+                        a.vdt = vdt + (size_t)(GUARD + 1) * pitch;
+                        void *params[] = {&a};
+                        CK(cudaLaunchKernel(v.fn, g2, b2, params, smem, 0));
+                    }
+                    CK(cudaEventRecord(e1));
+                    CK(cudaEventSynchronize(e1));
+                    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                    if (ms < best) best = ms;
+                }
+                int bad = 0;
+                for (int k = 0; k < 2; k++) {
+                    CK(cudaMemcpy(x.data(), f[k], elems * 4, cudaMemcpyDeviceToHost));
+                    CK(cudaMemcpy(y.data(), ref[k], elems * 4, cudaMemcpyDeviceToHost));
+                    bad += memcmp(x.data(), y.data(), elems * 4) != 0;
+                }
+                const double per = best / reps;
+                printf("%-20s CTA %3d x %2d rows: regs %3d spill %3zu B, %2d warps/SM  %8.4f ms/level  %7.1f Gpts/s  %s\n", v.n, gg[0], gg[1],
+                       fa.numRegs, fa.localSizeBytes, occ * gg[0] / 32, per, (double)nxe * nze / (per * 1e-3) / 1e9, bad ? "MISMATCH" : "bitwise OK");
+                fflush(stdout);
+            }
+        }
+        a.rows_per_cta = rpc;
     }
     /* ---- stand-alone Laplacian (config 1, 8 B/point): scalar vs packed */
     {
