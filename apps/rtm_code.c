@@ -101,6 +101,10 @@ int main(int argc, char **argv)
             ns, nt, t_dev, 3.0 * ns * nt * (double)ne / t_dev / 1e9, t_io, t_ctx, now_s() - t_start);
     snprintf(path, sizeof path, "%s/dir.image", in.tmpdir);
     write_floats(path, img, ni, "w");
+    /* dir.image_lap: the reference never computes it and writes zeros (fd-code.cu:477,542); FDW_IMAGE_LAP=1 fills it
+     * with the filter of models/3lay_mod/laplace.f90 on the GPU */
+    if (getenv("FDW_IMAGE_LAP") && atoi(getenv("FDW_IMAGE_LAP")) != 0)
+        FDW(fdw_image_laplacian(nx, nz, in.dx, in.dz, img, img_lap, prm.device));
     snprintf(path, sizeof path, "%s/dir.image_lap", in.tmpdir);
     write_floats(path, img_lap, ni, "w");
     fdw_destroy(ctx);

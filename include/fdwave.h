@@ -178,6 +178,11 @@ int fdw_stack_devptr(fdw_ctx *ctx, void **ptr, long long *pitch, int *rows);
  * [nxe][nze] host array, ring of width order/2 = 0. */
 int fdw_stencil(int order, int nxe, int nze, float dx, float dz, const float *in, float *out, int device);
 
+/* image post-filter: the 2nd-order Laplacian of cuda_reference_RTM/models/3lay_mod/laplace.f90:24-28
+ * applied to an [nx][nz] image on the GPU (one sweep; zero on the outermost ring).  rtm_code itself writes zeros
+ * into dir.image_lap (fd-code.cu:477,542) -- bin/rtm_code does the same unless FDW_IMAGE_LAP=1 asks for the filter. */
+int fdw_image_laplacian(int nx, int nz, float dx, float dz, const float *img, float *out, int device);
+
 /* ---------------------------------------------------------------- slab decomposition
  * A context created with slab_x0 < slab_x1 owns those rows of the extended
  * grid plus GUARD ghost rows on each side.  One time level is then driven in
@@ -237,7 +242,17 @@ int fdw_fields_download_local_async(fdw_ctx *ctx, int pair, float *newest, float
  *   fdw_peer_refresh   push the newest level's boundary rows (after an upload); all slabs call it
  *   fdw_peer_levels    nsteps levels of the current phase (fdw_shot_begin), asynchronous
  *   fdw_peer_fence     stream-side wait until every push addressed to this slab has landed;
- *                      call before zeroing / uploading / downloading after fdw_peer_levels */
+ *                      call before zeroing / uploading / downloading after fdw_peer_levels
+ * Contract of a (re)initialisation: zeroing or uploading the fields of a slab-decomposed run is COLLECTIVE --
+ * every slab initialises its buffers the same way (all zero, or all upload) and then calls fdw_peer_refresh,
+ * which re-publishes its boundary rows into the neighbours' ghost rows and raises "my buffers are ready".
+ * fdw_fields_zero leaves the ghost rows of an attached side alone (they belong to that neighbour's refresh,
+ * which may land before or after the memset), so a refresh is never wiped; a slab that skips the refresh
+ * leaves its neighbours with the previous run's ghost rows.
+ * Device-side waits (acquire of the neighbours' flags, grid barriers of the persistent / tile kernels) give up
+ * after FDW_TIMEOUT_MS of wall time (default 4000; %globaltimer, so independent of SM clocks and time slicing):
+ * the strip is then neither updated nor pushed on, and the next synchronising call returns FDW_ERR_CUDA.  A context
+ * whose level failed keeps consistent sponge counts / flag sequence; fdw_peer_attach clears the error state. */
 #define FDW_IPC_HANDLE_BYTES 64
 typedef struct fdw_peer_info {
     unsigned char field[4][FDW_IPC_HANDLE_BYTES];

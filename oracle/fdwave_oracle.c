@@ -585,3 +585,23 @@ void orc_rtm_shot(const orc_cpu_cfg *c, const float *v2, const float *srce, int 
     free(tx); free(tz); free(lap); free(P); free(PP); free(rwf);
     if (!swf_out) free(swf);
 }
+
+/* ---------------------------------------------------------------- image post-filter
+ * cuda_reference_RTM/models/3lay_mod/laplace.f90:24-28 (stand-alone Fortran tool, not called by any program):
+ *   o(iz,ix) = (i(iz+1,ix)-2.*i(iz,ix)+i(iz-1,ix))/(dz*dz) + (i(iz,ix+1)-2.*i(iz,ix)+i(iz,ix-1))/(dx*dx)
+ * for 2 <= ix <= nx-1, 2 <= iz <= nz-1, zero elsewhere; default REAL = float32, left-to-right evaluation.
+ * The file layout i(iz,ix), iz fastest, is our [ix][iz].  PARITY UNPINNED for this function: gfortran is not
+ * installed here and the reference ships no output of the tool (its committed ELF `laplace` is never run);
+ * the restatement follows the Fortran expression operation by operation in float32 without contraction. */
+void orc_image_laplacian(int nx, int nz, float dx, float dz, const float *img, float *out)
+{
+    const float dz2 = dz * dz, dx2 = dx * dx;
+    memset(out, 0, (size_t)nx * nz * sizeof(float));
+    for (int ix = 1; ix < nx - 1; ix++)
+        for (int iz = 1; iz < nz - 1; iz++) {
+            const float c = img[(size_t)ix * nz + iz];
+            const float tz = ((img[(size_t)ix * nz + iz + 1] - 2.f * c) + img[(size_t)ix * nz + iz - 1]) / dz2;
+            const float tx = ((img[(size_t)(ix + 1) * nz + iz] - 2.f * c) + img[(size_t)(ix - 1) * nz + iz]) / dx2;
+            out[(size_t)ix * nz + iz] = tz + tx;
+        }
+}

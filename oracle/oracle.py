@@ -59,6 +59,7 @@ def lib():
         L.orc_stencil.argtypes = [C.c_int] * 3 + [C.c_float, C.c_float, f32p, f32p]
         L.orc_gpu_forward.argtypes = [C.POINTER(GpuCfg), f32p, f32p, f32p, f32p, C.c_int, C.c_int]
         L.orc_gpu_back.argtypes = [C.POINTER(GpuCfg), f32p, f32p, f32p, f32p, C.c_int, f32p]
+        L.orc_image_laplacian.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, f32p, f32p]
         L.orc_fd_step.argtypes = [C.c_int] * 3 + [f32p, f32p, f32p, f32p] + [C.c_float] * 3
         L.orc_mod_shot.argtypes = [C.POINTER(CpuCfg), f32p, f32p, C.c_int, C.c_int, C.c_int, f32p]
         L.orc_rtm_shot.argtypes = [C.POINTER(CpuCfg), f32p, f32p, C.c_int, C.c_int, C.c_int, f32p,
@@ -203,3 +204,11 @@ def rtm_shot(cfg, v2, srce, sx, sz, gz, dobs_all, is_=0, want_swf=False):
     lib().orc_rtm_shot(C.byref(cfg), v2, srce, sx, sz, gz, dobs_all, ns, is_, imloc,
                        swf.ctypes.data if want_swf else None)
     return (imloc, swf) if want_swf else imloc
+
+
+def image_laplacian(img, dx, dz):
+    """laplace.f90:24-28 on an [nx][nz] image (parity unpinned: no gfortran, no shipped output)"""
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty_like(img)
+    lib().orc_image_laplacian(img.shape[0], img.shape[1], dx, dz, img, out)
+    return out

@@ -94,6 +94,7 @@ SIGNATURES = {
     "fdw_model_shot": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p]),
     "fdw_rtm_shot_cpu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_int, C.c_int, f32p]),
     "fdw_stencil": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, f32p, f32p, C.c_int]),
+    "fdw_image_laplacian": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, f32p, f32p, C.c_int]),
     "fdw_shot_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _optf32, C.c_int, C.c_int]),
     "fdw_shot_end": (C.c_int, [C.c_void_p, f32p]),
     "fdw_step_begin": (C.c_int, [C.c_void_p, C.c_int]),

@@ -79,6 +79,7 @@ struct RecLaunch {
     int par = 0;                       /* 1: independent of the previous launch of its lane (runs beside it) */
     StepArgs a;
     const unsigned *w_mine = nullptr; unsigned v = 0; int need_lo = 0, need_hi = 0; int *err = nullptr;
+    unsigned long long tmo = 0;
     unsigned *s_lo = nullptr, *s_hi = nullptr;
 };
 
@@ -136,6 +137,7 @@ struct fdw_ctx {
     unsigned *flags_d = nullptr; /* written by the neighbours: [0] by the lower one, [1] by the upper one */
     unsigned *pcount_d = nullptr; /* CTAs of the current level's boundary launches that have finished */
     int fuse_flags = 1;          /* acquire/release inside the boundary kernels instead of separate launches */
+    unsigned long long timeout_ns = 4000000000ull; /* device-side waits give up after this long (FDW_TIMEOUT_MS) */
     unsigned peer_seq = 0;       /* boundary-row pushes issued so far (lock-step on all slabs) */
     long long peer_waits = 0;
     /* CUDA-graph replay of the level loop: when `rec` is set, launches are recorded instead of issued */
@@ -198,17 +200,19 @@ __global__ void k_peer_signal(unsigned *flag_lo, unsigned *flag_hi, unsigned v)
 #endif
 }
 
-__global__ void k_peer_wait(const unsigned *mine, unsigned v, int need_lo, int need_hi, int *error_flag)
+__global__ void k_peer_wait(const unsigned *mine, unsigned v, int need_lo, int need_hi, int *error_flag,
+                            unsigned long long timeout_ns)
 {
 #ifdef FDW_EMU
     /* the host stand-in runs everything synchronously: an unmet flag is a protocol error */
     if ((need_lo && !emu_wait_flag(mine + 0, v)) || (need_hi && !emu_wait_flag(mine + 1, v))) *error_flag = 2;
 #else
-    const long long t0 = clock64();
+    const unsigned long long t0 = fdw::wall_ns();
     for (int s = 0; s < 2; s++) {
         if (!(s == 0 ? need_lo : need_hi)) continue;
+        unsigned spins = 0;
         while (*((volatile const unsigned *)mine + s) < v) {
-            if (clock64() - t0 > (1LL << 33)) { /* ~4 s: never hang the GPU on a lost neighbour */
+            if ((++spins & 255u) == 0 && fdw::wall_ns() - t0 > timeout_ns) { /* never hang the GPU on a lost neighbour */
                 atomicExch(error_flag, 2);
                 return;
             }
@@ -222,7 +226,7 @@ __global__ void k_peer_wait(const unsigned *mine, unsigned v, int need_lo, int n
 static void thunk_peer_signal(void **a) { k_peer_signal(*(unsigned **)a[0], *(unsigned **)a[1], *(unsigned *)a[2]); }
 static void thunk_peer_wait(void **a)
 {
-    k_peer_wait(*(const unsigned **)a[0], *(unsigned *)a[1], *(int *)a[2], *(int *)a[3], *(int **)a[4]);
+    k_peer_wait(*(const unsigned **)a[0], *(unsigned *)a[1], *(int *)a[2], *(int *)a[3], *(int **)a[4], *(unsigned long long *)a[5]);
 }
 static void thunk_scale_rows(void **a) { k_scale_rows(*(float **)a[0], *(long long *)a[1], *(float *)a[2]); }
 static void thunk_materialize(void **a)
@@ -618,6 +622,7 @@ static void persist_args(fdw_ctx *c, int pair, StepArgs &base, bool tap, bool so
     pa->hist_slice = (long long)(c->nli > 0 ? c->nli : 1) * c->pitch;
     pa->barrier = c->barrier_d;
     pa->error_flag = c->errflag_d;
+    pa->timeout_ns = c->timeout_ns;
 }
 
 static bool small_whole_grid(const fdw_ctx *c, const StepArgs &base)
@@ -691,6 +696,7 @@ static int try_persistent(fdw_ctx *c, int recipe, int epi, bool sponge, bool sou
     pa.hist_slice = (long long)(c->nli > 0 ? c->nli : 1) * c->pitch;
     pa.barrier = c->barrier_d;
     pa.error_flag = c->errflag_d;
+    pa.timeout_ns = c->timeout_ns;
     if (cudaMemsetAsync(c->barrier_d, 0, sizeof(unsigned), c->stream) != cudaSuccess) return 0;
     dim3 grid(gx, (rows + rpc - 1) / rpc, 1), block(nthreads, 1, 1);
     void *params[] = {&pa};
@@ -738,14 +744,17 @@ static int materialize(fdw_ctx *c, Field &f)
     int lo = -GUARD, hi = c->nloc + GUARD;
     if (c->gx0 + lo < 0) lo = -c->gx0;
     if (c->gx0 + hi > c->nxe) hi = c->nxe - c->gx0;
-    dim3 block(128), grid((c->nze + 127) / 128, hi - lo);
     float *r0 = f.r0;
     long long pitch = c->pitch;
     const float *tz = c->tz, *tx = c->tx;
     int cnt = f.pend;
-    void *params[] = {&r0, &pitch, &c->nze, &lo, &hi, &c->gx0, &tz, &tx, &c->tx_jlim, &c->tz_ilim, &cnt};
-    CU(cudaLaunchKernel(FDW_KPTR(k_materialize, thunk_materialize), grid, block, params, 0, c->stream));
-    c->launches++;
+    for (int b0 = lo; b0 < hi; b0 += 65535) { /* gridDim.y limit: bands of at most 65535 rows */
+        int b1 = b0 + 65535 < hi ? b0 + 65535 : hi;
+        dim3 block(128), grid((c->nze + 127) / 128, b1 - b0);
+        void *params[] = {&r0, &pitch, &c->nze, &b0, &b1, &c->gx0, &tz, &tx, &c->tx_jlim, &c->tz_ilim, &cnt};
+        CU(cudaLaunchKernel(FDW_KPTR(k_materialize, thunk_materialize), grid, block, params, 0, c->stream));
+        c->launches++;
+    }
     f.pend = 0;
     return FDW_OK;
 }
@@ -761,7 +770,13 @@ static int field_alloc(fdw_ctx *c, Field *f)
 
 static int field_zero(fdw_ctx *c, Field *f)
 {
-    CU(cudaMemsetAsync(f->base, 0, c->field_elems * sizeof(float), c->stream));
+    /* With a neighbour attached, the ghost rows on that side belong to the neighbour's fdw_peer_refresh, which
+     * may land before or after this memset: they are left alone (the refresh that must follow a zero on every
+     * slab overwrites them), only the owned rows and the ghost rows of a physical grid edge are cleared. */
+    const size_t ghost = (size_t)(GUARD + 1) * c->pitch;
+    float *lo = f->base + (c->peer[0].on ? ghost : 0);
+    float *hi = f->base + c->field_elems - (c->peer[1].on ? ghost : 0);
+    CU(cudaMemsetAsync(lo, 0, (size_t)(hi - lo) * sizeof(float), c->stream));
     f->pend = 0;
     return FDW_OK;
 }
@@ -885,6 +900,7 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
     if (const char *e = getenv("FDW_FUSE_FLAGS")) c->fuse_flags = atoi(e);
+    if (const char *e = getenv("FDW_TIMEOUT_MS")) c->timeout_ns = 1000000ull * (unsigned long long)atoll(e);
 
     /* coefficients and scalars: fd-code.cu:203-217 / fd.c:12-16 */
     float coefs[9];
@@ -1527,6 +1543,57 @@ extern "C" int fdw_stencil(int order, int nxe, int nze, float dx, float dz, cons
     return rc;
 }
 
+/* ------------------------------------------------------------------ image post-filter (laplace.f90:24-28) */
+__global__ void k_image_lap(const float *img, float *out, int nx, int nz, float dx2, float dz2)
+{
+    const int iz = blockIdx.x * blockDim.x + threadIdx.x, ix = blockIdx.y;
+    if (iz >= nz || ix >= nx) return;
+    float o = 0.0f;
+    if (ix >= 1 && ix < nx - 1 && iz >= 1 && iz < nz - 1) {
+        const float *p = img + (size_t)ix * nz + iz;
+        const float c = p[0];
+        const float tz = __fdiv_rn(__fadd_rn(__fsub_rn(p[1], __fmul_rn(2.0f, c)), p[-1]), dz2);
+        const float tx = __fdiv_rn(__fadd_rn(__fsub_rn(p[nz], __fmul_rn(2.0f, c)), p[-nz]), dx2);
+        o = __fadd_rn(tz, tx);
+    }
+    out[(size_t)ix * nz + iz] = o;
+}
+#ifdef FDW_EMU
+static void thunk_image_lap(void **a)
+{
+    k_image_lap(*(const float **)a[0], *(float **)a[1], *(int *)a[2], *(int *)a[3], *(float *)a[4], *(float *)a[5]);
+}
+#endif
+
+extern "C" int fdw_image_laplacian(int nx, int nz, float dx, float dz, const float *img, float *out, int device)
+{
+    if (!img || !out || nx < 1 || nz < 1) return FDW_ERR_ARG;
+    int ndev = fdw_device_count();
+    if (ndev < 1 || device < 0 || device >= ndev) {
+        fdw_set_error("fdw_image_laplacian: CUDA device %d not available (%d visible); libfdwave has no CPU path", device, ndev);
+        return FDW_ERR_CUDA;
+    }
+    CU(cudaSetDevice(device));
+    const size_t bytes = (size_t)nx * nz * sizeof(float);
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, bytes));
+    if (cudaMalloc(&d_out, bytes) != cudaSuccess) { cudaFree(d_in); fdw_set_error("fdw_image_laplacian: out of device memory"); return FDW_ERR_NOMEM; }
+    int rc = FDW_OK;
+    float dx2 = dx * dx, dz2 = dz * dz;
+    const float *cin = d_in;
+    void *params[] = {&cin, &d_out, &nx, &nz, &dx2, &dz2};
+    if (nx > 65535) { cudaFree(d_in); cudaFree(d_out); fdw_set_error("fdw_image_laplacian: nx > 65535 not supported"); return FDW_ERR_UNSUPPORTED; }
+    if (cudaMemcpy(d_in, img, bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaLaunchKernel(FDW_KPTR(k_image_lap, thunk_image_lap), dim3((nz + 127) / 128, nx), dim3(128), params, 0, 0) != cudaSuccess ||
+        cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fdw_set_error("fdw_image_laplacian: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = FDW_ERR_CUDA;
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ slab decomposition */
 extern "C" int fdw_step_begin(fdw_ctx *c, int it)
 {
@@ -1723,6 +1790,8 @@ extern "C" int fdw_peer_attach(fdw_ctx *c, const fdw_peer_info *lo, const fdw_pe
         }
     }
     c->peer_seq = 0;
+    CU(cudaMemsetAsync(c->errflag_d, 0, sizeof(int), c->stream)); /* a fresh attachment starts without a stale time-out */
+    CU(cudaMemsetAsync(c->pcount_d, 0, sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(c->flags_d, 0, 2 * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return FDW_OK;
@@ -1751,11 +1820,11 @@ static int peer_wait(fdw_ctx *c, cudaStream_t st)
         RecLaunch r;
         r.kern = FDW_KPTR(k_peer_wait, thunk_peer_wait); r.grid = dim3(1); r.block = dim3(1);
         r.side = st == c->side && st != c->stream; r.kind = 1; r.level = c->rec_level;
-        r.w_mine = mine; r.v = v; r.need_lo = need_lo; r.need_hi = need_hi; r.err = c->errflag_d;
+        r.w_mine = mine; r.v = v; r.need_lo = need_lo; r.need_hi = need_hi; r.err = c->errflag_d; r.tmo = c->timeout_ns;
         c->rec->push_back(r);
         return FDW_OK;
     }
-    void *params[] = {&mine, &v, &need_lo, &need_hi, &c->errflag_d};
+    void *params[] = {&mine, &v, &need_lo, &need_hi, &c->errflag_d, &c->timeout_ns};
     CU(cudaLaunchKernel(FDW_KPTR(k_peer_wait, thunk_peer_wait), dim3(1), dim3(1), params, 0, st));
     return FDW_OK;
 }
@@ -1785,6 +1854,9 @@ static int peer_signal(fdw_ctx *c, cudaStream_t st)
 static int peer_level(fdw_ctx *c, int it)
 {
     const int nc = c->ncol4;
+    /* a failed level must leave this slab's sponge counts and flag sequence where its neighbours' are */
+    const int pend_n0 = c->f[c->newest[0]].pend, pend_o0 = c->f[c->older[0]].pend;
+    const unsigned seq0 = c->peer_seq;
     CHECK(fdw_step_begin(c, it));
     StepArgs a = c->step_args;
     const int epi = phase_epi(c->phase);
@@ -1819,6 +1891,7 @@ static int peer_level(fdw_ctx *c, int it)
     if (fused) {
         a.pw_flags = c->flags_d; a.pw_v = c->peer_seq; a.pw_lo = c->peer[0].on; a.pw_hi = c->peer[1].on;
         a.pw_err = c->errflag_d;
+        a.pw_timeout_ns = c->timeout_ns;
         c->peer_seq++;
         a.ps_lo = c->peer[0].on ? c->peer[0].flags + 1 : nullptr; /* this slab is the lower neighbour's upper one */
         a.ps_hi = c->peer[1].on ? c->peer[1].flags + 0 : nullptr;
@@ -1836,7 +1909,13 @@ static int peer_level(fdw_ctx *c, int it)
     if (rc == FDW_OK && ev && cudaEventRecord(c->ev_pjoin, c->side) != cudaSuccess) rc = FDW_ERR_CUDA;
     if (rc == FDW_OK) rc = launch_level(c, c->step_args, c->prm.recipe, epi, ilo, ihi, c->stream);
     if (rc == FDW_OK && ev && cudaStreamWaitEvent(c->stream, c->ev_pjoin, 0) != cudaSuccess) rc = FDW_ERR_CUDA;
-    if (rc != FDW_OK) { c->step_open = false; return rc; }
+    if (rc != FDW_OK) {
+        c->step_open = false;
+        c->f[c->newest[0]].pend = pend_n0;
+        c->f[c->older[0]].pend = pend_o0;
+        c->peer_seq = seq0;
+        return rc;
+    }
     return fdw_step_end(c);
 }
 
@@ -1862,13 +1941,13 @@ static void node_params(RecLaunch &r, cudaKernelNodeParams *kp, void **slots)
     kp->func = const_cast<void *>(r.kern);
     kp->gridDim = r.grid; kp->blockDim = r.block; kp->sharedMemBytes = 0; kp->extra = nullptr;
     if (r.kind == 0) { slots[0] = &r.a; }
-    else if (r.kind == 1) { slots[0] = &r.w_mine; slots[1] = &r.v; slots[2] = &r.need_lo; slots[3] = &r.need_hi; slots[4] = &r.err; }
+    else if (r.kind == 1) { slots[0] = &r.w_mine; slots[1] = &r.v; slots[2] = &r.need_lo; slots[3] = &r.need_hi; slots[4] = &r.err; slots[5] = &r.tmo; }
     else { slots[0] = &r.s_lo; slots[1] = &r.s_hi; slots[2] = &r.v; }
     kp->kernelParams = slots;
 #ifdef FDW_EMU
     /* the host stand-in has to copy the argument values; it is told their sizes through `extra` */
     static size_t sz_step[] = {sizeof(StepArgs), 0};
-    static size_t sz_wait[] = {sizeof(const unsigned *), sizeof(unsigned), sizeof(int), sizeof(int), sizeof(int *), 0};
+    static size_t sz_wait[] = {sizeof(const unsigned *), sizeof(unsigned), sizeof(int), sizeof(int), sizeof(int *), sizeof(unsigned long long), 0};
     static size_t sz_signal[] = {sizeof(unsigned *), sizeof(unsigned *), sizeof(unsigned), 0};
     kp->extra = (void **)(r.kind == 0 ? sz_step : r.kind == 1 ? sz_wait : sz_signal);
 #endif
@@ -1903,7 +1982,7 @@ static int graph_build(fdw_ctx *c, std::vector<RecLaunch> &rec)
     for (size_t i = 0; i < rec.size(); i++) {
         RecLaunch &r = rec[i];
         if (r.level != level) { CHECK(close_level()); level = r.level; }
-        cudaKernelNodeParams kp; void *slots[5];
+        cudaKernelNodeParams kp; void *slots[6];
         node_params(r, &kp, slots);
         const int ln = r.side;
         /* lane order within the level; a lane's first node hangs off the previous level's join; a `par`
@@ -1938,7 +2017,7 @@ static int peer_level_pair_graph(fdw_ctx *c, int it)
         CHECK(graph_build(c, rec));
     } else {
         for (size_t i = 0; i < rec.size(); i++) {
-            cudaKernelNodeParams kp; void *slots[5];
+            cudaKernelNodeParams kp; void *slots[6];
             node_params(rec[i], &kp, slots);
             CU(cudaGraphExecKernelNodeSetParams(c->lexec, c->lnodes[i], &kp));
         }

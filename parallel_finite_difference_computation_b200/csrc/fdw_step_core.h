@@ -108,6 +108,7 @@ struct StepArgs {
     int *pw_err;
     unsigned *ps_lo, *ps_hi, *ps_count;
     unsigned ps_v, ps_total;
+    unsigned long long pw_timeout_ns; /* the acquire gives up (error flag 2, no update, no push) after this wall time */
 };
 
 /* the few quantities that change from one time level to the next; the ordinary kernels copy
@@ -153,6 +154,7 @@ struct PersistArgs {
     long long hist_slice;
     unsigned *barrier;  /* zeroed before the launch */
     int *error_flag;
+    unsigned long long timeout_ns; /* device-wide waits give up after this wall time */
 };
 
 /* the Level of launch-relative level l, in closed form (see the host bookkeeping in step_pair) */
@@ -211,6 +213,18 @@ FDW_HD float leap(float p, float pp, float t)
     double d = 2.0 * (double)p - (double)pp;
     return (float)(d + (double)t);
 }
+#endif
+
+/* wall-clock nanoseconds (time-outs of device-side waits must not depend on the SM clock or on time slicing) */
+#ifdef __CUDA_ARCH__
+FDW_HD unsigned long long wall_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#else
+FDW_HD unsigned long long wall_ns() { return 0; }
 #endif
 
 /* ---- packed FP32x2 arithmetic (sm_100a FMUL2 / FFMA2: two IEEE round-to-nearest results per

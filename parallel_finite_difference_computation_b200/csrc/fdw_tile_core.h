@@ -48,10 +48,11 @@ __device__ __forceinline__ unsigned long long tile_globaltimer()
 }
 
 /* device-wide barrier of the co-resident grid: everything this CTA stored before it is visible to every
- * CTA after it.  Wall-clock (globaltimer) bail-out after ~2 s so that a lost CTA can never hang the GPU. */
+ * CTA after it.  Wall-clock (globaltimer) bail-out after pa.timeout_ns so that a lost CTA can never hang the GPU. */
 /* `lost` is a shared-memory word of the CTA (zeroed at kernel start): a time-out is reported to the host
  * through error_flag and to the CTA's own threads through `lost`, so that the common path reads no global memory */
-__device__ __forceinline__ bool tile_grid_barrier(unsigned *ctr, unsigned target, int *error_flag, volatile int *lost)
+__device__ __forceinline__ bool tile_grid_barrier(unsigned *ctr, unsigned target, int *error_flag, volatile int *lost,
+                                                  unsigned long long timeout_ns)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -60,7 +61,7 @@ __device__ __forceinline__ bool tile_grid_barrier(unsigned *ctr, unsigned target
             const unsigned long long t0 = tile_globaltimer();
             unsigned spins = 0;
             while (tile_ld_acquire(ctr) < target) {
-                if ((++spins & 1023u) == 0 && tile_globaltimer() - t0 > 2000000000ull) {
+                if ((++spins & 1023u) == 0 && tile_globaltimer() - t0 > timeout_ns) {
                     atomicExch(error_flag, 1);
                     *lost = 1;
                     break;
@@ -86,7 +87,7 @@ __device__ __forceinline__ void tile_st_release(unsigned *p, unsigned v)
  * copy that holds level l-1 only after its neighbours have published level l, i.e. after they finished reading
  * level l-1. */
 __device__ __forceinline__ bool tile_neighbour_sync(unsigned *flags, const TileArgs &ta, unsigned level, int *error_flag,
-                                                    volatile int *lost)
+                                                    volatile int *lost, unsigned long long timeout_ns)
 {
     const int me = blockIdx.x, tx = me % ta.ntx, ty = me / ta.ntx;
     __syncthreads();
@@ -104,7 +105,7 @@ __device__ __forceinline__ bool tile_neighbour_sync(unsigned *flags, const TileA
             const unsigned long long t0 = tile_globaltimer();
             unsigned spins = 0;
             while (tile_ld_acquire(flags + 32 * nb) < level) {
-                if ((++spins & 1023u) == 0 && tile_globaltimer() - t0 > 2000000000ull) {
+                if ((++spins & 1023u) == 0 && tile_globaltimer() - t0 > timeout_ns) {
                     atomicExch(error_flag, 1);
                     *lost = 1;
                     break;
@@ -118,8 +119,8 @@ __device__ __forceinline__ bool tile_neighbour_sync(unsigned *flags, const TileA
 
 __device__ __forceinline__ bool tile_sync(const TileArgs &ta, unsigned level, unsigned nblk, volatile int *lost)
 {
-    if (ta.dbg & 8) return tile_grid_barrier(ta.pa.barrier, level * nblk, ta.pa.error_flag, lost);
-    return tile_neighbour_sync(ta.flags, ta, level, ta.pa.error_flag, lost);
+    if (ta.dbg & 8) return tile_grid_barrier(ta.pa.barrier, level * nblk, ta.pa.error_flag, lost, ta.pa.timeout_ns);
+    return tile_neighbour_sync(ta.flags, ta, level, ta.pa.error_flag, lost, ta.pa.timeout_ns);
 }
 
 struct TileGeom {

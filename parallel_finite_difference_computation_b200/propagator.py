@@ -216,3 +216,13 @@ def stencil(p, order=8, dx=10.0, dz=10.0, device=0, lib=None):
     out = np.empty_like(p)
     _lib.check(L, L.fdw_stencil(order, p.shape[0], p.shape[1], dx, dz, p, out, device))
     return out
+
+
+def image_laplacian(img, dx=10.0, dz=10.0, device=0, lib=None):
+    """the image post-filter of cuda_reference_RTM/models/3lay_mod/laplace.f90:24-28 on the GPU: 2nd-order Laplacian
+    of an [nx][nz] image, zero on the outermost ring"""
+    L = lib if lib is not None else _lib.load()
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty_like(img)
+    _lib.check(L, L.fdw_image_laplacian(img.shape[0], img.shape[1], dx, dz, img, out, device))
+    return out

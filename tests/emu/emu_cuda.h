@@ -44,6 +44,8 @@ struct cudaDeviceProp { int multiProcessorCount; };
 
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
 
 cudaError_t cudaSetDevice(int);
 cudaError_t cudaGetDeviceCount(int *);
@@ -55,6 +57,7 @@ template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { retur
 cudaError_t cudaFree(void *);
 cudaError_t cudaMemsetAsync(void *, int, size_t, cudaStream_t);
 cudaError_t cudaMemcpyAsync(void *, const void *, size_t, cudaMemcpyKind, cudaStream_t);
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind k) { return cudaMemcpyAsync(d, s, n, k, (cudaStream_t)0); }
 cudaError_t cudaMemcpy2DAsync(void *, size_t, const void *, size_t, size_t, size_t, cudaMemcpyKind, cudaStream_t);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *, unsigned);
 cudaError_t cudaStreamSynchronize(cudaStream_t);

@@ -220,3 +220,19 @@ def test_reference_rtm_main_relinked_against_gpufam_shim(tmp_path, dims):
         c = np.fromfile(ref / "out" / "dir.image", np.float32).reshape(nx, nz)
         print("relinked vs reference CUDA program: rel-L2 %.3g" % PC.rel_l2(b, c))
         assert PC.rel_l2(b, c) <= 5e-3
+
+
+def test_rtm_code_image_lap_opt_in(tmp_path):
+    """dir.image_lap: zeros by default like the reference (fd-code.cu:477,542); FDW_IMAGE_LAP=1 fills it with the
+    laplace.f90 filter of dir.image"""
+    nx, nz, nb, nt, ns = 61, 47, 16, 120, 1
+    d = tmp_path / "case"
+    os.makedirs(d)
+    _write_rtm_case(str(d), nx, nz, nb, nt, ns, seed=8)
+    run([os.path.join(BIN, "rtm_code"), "./input.dat"], d)
+    assert not np.fromfile(d / "out" / "dir.image_lap", np.float32).any()
+    run([os.path.join(BIN, "rtm_code"), "./input.dat"], d, env=dict(os.environ, FDW_IMAGE_LAP="1"))
+    img = np.fromfile(d / "out" / "dir.image", np.float32).reshape(nx, nz)
+    lap = np.fromfile(d / "out" / "dir.image_lap", np.float32).reshape(nx, nz)
+    assert np.abs(img).max() > 0
+    PC.assert_bit_equal(lap, O.image_laplacian(img, 10.0, 10.0), "dir.image_lap")

@@ -166,6 +166,14 @@ def test_shot_pipeline_device_stack_equals_sequential_loop(lib, small, monkeypat
     assert np.abs(seq).max() > 0
 
 
+@pytest.mark.parametrize("shape", [(151, 151), (37, 90), (3, 3), (2, 5), (1030, 517)])
+def test_image_laplacian_bit_exact(lib, shape):
+    """the image post-filter (laplace.f90:24-28) on the GPU vs the oracle"""
+    rng = np.random.default_rng(9)
+    img = rng.standard_normal(shape).astype(np.float32)
+    PC.assert_bit_equal(fdw.image_laplacian(img, dx=25.0, dz=8.0), O.image_laplacian(img, 25.0, 8.0), "image laplacian")
+
+
 # ------------------------------------------------------------------ reference golden files
 def test_golden_3lay_mod_seismogram_and_image(lib, golden_dir):
     """mod_main + rtm_main on build/3lay_mod reproduce the reference's shipped

@@ -122,3 +122,19 @@ def test_cpu_family_functions_vs_reference_objects(refvec):
 
 def test_gpu_launch_extents(refvec):
     assert tuple(refvec["gpu_launch_extents_415x295_nb50"]) == (408, 288, 48)
+
+
+def test_image_laplacian_matches_the_fortran_expression():
+    """oracle of the image post-filter (laplace.f90:24-28) against an independent float32 numpy restatement of the
+    same left-to-right expression; ring of width 1 is zero.  (Parity unpinned: no gfortran here, no shipped output.)"""
+    rng = np.random.default_rng(4)
+    for nx, nz, dx, dz in ((151, 151, 10.0, 10.0), (37, 90, 25.0, 8.0), (3, 3, 1.0, 1.0), (2, 5, 10.0, 10.0)):
+        img = rng.standard_normal((nx, nz)).astype(np.float32)
+        got = O.image_laplacian(img, dx, dz)
+        want = np.zeros_like(img)
+        f = np.float32
+        c = img[1:-1, 1:-1]
+        tz = ((img[1:-1, 2:] - f(2.0) * c) + img[1:-1, :-2]) / (f(dz) * f(dz))
+        tx = ((img[2:, 1:-1] - f(2.0) * c) + img[:-2, 1:-1]) / (f(dx) * f(dx))
+        want[1:-1, 1:-1] = tz + tx
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
