@@ -47,6 +47,28 @@ def layered(nxe, nze):
     return ve * ve
 
 
+class quiet_stdout:
+    """the reference's CUDA library printf()s its progress ("* it = 100 / 1700") on the C stdout: send file
+    descriptor 1 to /dev/null while its code runs so that bench.py's stdout stays ONE JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+        return self
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
 def _roof(gpts, bytes_per_point):
     gbs = gpts * bytes_per_point
     return {"bytes_per_point": bytes_per_point, "achieved_gbs": gbs, "frac_of_measured_hbm_peak": gbs / hbm_peak()}
@@ -114,18 +136,19 @@ def c2_small_models(device, with_reference=True):
              "forward_gpts": nxe * nze * nt / (best_f * 1e-3) / 1e9, "backward_gpts": 2.0 * nxe * nze * nt / (best_b * 1e-3) / 1e9}
         if ref is not None:
             try:
-                ref.fd_init(8, nxe, nze, nb, nb, nt, 1, 0.75, 10.0, 10.0, 0.001)
-                tf = tb = 1e30
-                for _ in range(2):
-                    z = lambda: np.zeros((nxe, nze), np.float32)
-                    P, PP = z(), z()
-                    t0 = time.perf_counter()
-                    ref.fd_forward(8, P, PP, v2, nt, 0, nb, [nb + 10], srce)
-                    t1 = time.perf_counter()
-                    im = np.zeros((nx, nz), np.float32)
-                    ref.fd_back(8, z(), z(), z(), z(), v2, nt, 0, nb, nb, np.stack([P, PP]), im, dobs.reshape(1, -1).copy())
-                    t2 = time.perf_counter()
-                    tf, tb = min(tf, t1 - t0), min(tb, t2 - t1)
+                with quiet_stdout():
+                    ref.fd_init(8, nxe, nze, nb, nb, nt, 1, 0.75, 10.0, 10.0, 0.001)
+                    tf = tb = 1e30
+                    for _ in range(2):
+                        z = lambda: np.zeros((nxe, nze), np.float32)
+                        P, PP = z(), z()
+                        t0 = time.perf_counter()
+                        ref.fd_forward(8, P, PP, v2, nt, 0, nb, [nb + 10], srce)
+                        t1 = time.perf_counter()
+                        im = np.zeros((nx, nz), np.float32)
+                        ref.fd_back(8, z(), z(), z(), z(), v2, nt, 0, nb, nb, np.stack([P, PP]), im, dobs.reshape(1, -1).copy())
+                        t2 = time.perf_counter()
+                        tf, tb = min(tf, t1 - t0), min(tb, t2 - t1)
                 r.update(reference_cuda_forward_us_per_level=tf / nt * 1e6, reference_cuda_backward_us_per_level=tb / nt * 1e6,
                          speedup_forward=tf * 1e3 / best_f, speedup_backward=tb * 1e3 / best_b,
                          reference_note="fd_forward / fd_back of cuda_reference_RTM/src/fd-code.cu rebuilt for sm_100 "
@@ -302,16 +325,18 @@ def gpu_reference(n=8192, device=0):
             return {"unavailable": "oracle/_ref/libref_gpufam.so not present"}
         g = R.GpuFam()
         nb, nt_a, nt_b = 40, 4, 24
-        g.fd_init(8, n, n, nb, nb, nt_b, 1, 0.75, 10.0, 10.0, 0.001)
+        with quiet_stdout():
+            g.fd_init(8, n, n, nb, nb, nt_b, 1, 0.75, 10.0, 10.0, 0.001)
         v2 = layered(n, n)
         srce = fdw.host.ricker_wavelet(nt_b, 0.001, 20.0, fdw.FAMILY_GPU)
         P, PP = np.zeros((n, n), np.float32), np.zeros((n, n), np.float32)
-        g.fd_forward(8, P, PP, v2, nt_a, 0, nb, [n // 2], srce)  # warm-up
         ts = {}
-        for nt in (nt_a, nt_b, nt_a, nt_b):
-            t0 = time.perf_counter()
-            g.fd_forward(8, P, PP, v2, nt, 0, nb, [n // 2], srce)
-            ts[nt] = min(ts.get(nt, 1e30), time.perf_counter() - t0)
+        with quiet_stdout():
+            g.fd_forward(8, P, PP, v2, nt_a, 0, nb, [n // 2], srce)  # warm-up
+            for nt in (nt_a, nt_b, nt_a, nt_b):
+                t0 = time.perf_counter()
+                g.fd_forward(8, P, PP, v2, nt, 0, nb, [n // 2], srce)
+                ts[nt] = min(ts.get(nt, 1e30), time.perf_counter() - t0)
         per_level = (ts[nt_b] - ts[nt_a]) / (nt_b - nt_a)
         gpts = float(n) * n / per_level / 1e9
         return {"what": "reference CUDA kernels (cuda_reference_RTM fd_forward, sm_100 rebuild), %d x %d, per level = "

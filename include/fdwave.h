@@ -288,6 +288,7 @@ long long fdw_launch_count(fdw_ctx *ctx);
 #define FDW_COUNTER_GRAPH_REPLAYS 1   /* CUDA-graph replays of the peer-memory level loop */
 #define FDW_COUNTER_PERSIST_LAUNCHES 2 /* phases run by the persistent (L2-resident) kernel */
 #define FDW_COUNTER_TILE_LAUNCHES 3    /* phases run by the shared-memory tile kernel */
+#define FDW_COUNTER_PSLAB_LAUNCHES 4   /* level runs of a thin slab done by ONE launch of the persistent slab kernel */
 long long fdw_counter(fdw_ctx *ctx, int which);
 /* standalone Laplacian on device-resident data of pair 0 (newest -> older), for benchmarks */
 int fdw_laplacian_device(fdw_ctx *ctx);

@@ -18,7 +18,7 @@ RECIPE_G, RECIPE_C, RECIPE_FAST = 0, 1, 2
 TAPER_NONE, TAPER_TOP, TAPER_FOUR = 0, 1, 2
 SRC_POINT, SRC_GAUSS7 = 0, 1
 PHASE_PLAIN, PHASE_MODEL, PHASE_RTM_FWD, PHASE_RTM_BWD = 0, 1, 2, 3
-COUNTER_LAUNCHES, COUNTER_GRAPH_REPLAYS, COUNTER_PERSIST_LAUNCHES, COUNTER_TILE_LAUNCHES = 0, 1, 2, 3
+COUNTER_LAUNCHES, COUNTER_GRAPH_REPLAYS, COUNTER_PERSIST_LAUNCHES, COUNTER_TILE_LAUNCHES, COUNTER_PSLAB_LAUNCHES = 0, 1, 2, 3, 4
 
 f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 

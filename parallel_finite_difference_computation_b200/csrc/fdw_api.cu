@@ -33,6 +33,7 @@ using fdw::GUARD;
 using fdw::StepArgs;
 using fdw::PersistArgs;
 using fdw::TileArgs;
+using fdw::PSlabArgs;
 
 /* ------------------------------------------------------------------ errors */
 static thread_local char g_err[512] = "";
@@ -120,6 +121,9 @@ struct fdw_ctx {
     int *errflag_d = nullptr;
     int coop = 0;                      /* device supports cooperative launches */
     long long persist_limit = 1LL << 18; /* float4 columns x rows below which phases run persistently */
+    int use_pslab = 1;                   /* persistent slab kernel for thin slabs (FDW_PSLAB=0: graph-replayed launches) */
+    long long pslab_limit = 1LL << 20;   /* float4 columns x rows below which a slab's levels run in one launch */
+    long long pslab_launches = 0;
     int use_tile = 1;                    /* shared-memory tile kernel for those grids (FDW_TILE=0: L2-resident persistent kernel) */
     int smem_optin = 0;                  /* largest dynamic shared memory per CTA */
     long long persist_launches = 0;
@@ -269,6 +273,17 @@ static const void *tile_kernel(int order, int recipe, int epi)
     case 4: return fdw_tile_kernel_o4(recipe, epi);
     case 6: return fdw_tile_kernel_o6(recipe, epi);
     case 8: return fdw_tile_kernel_o8(recipe, epi);
+    }
+    return nullptr;
+}
+
+static const void *pslab_kernel(int order, int recipe, int epi)
+{
+    switch (order) {
+    case 2: return fdw_pslab_kernel_o2(recipe, epi);
+    case 4: return fdw_pslab_kernel_o4(recipe, epi);
+    case 6: return fdw_pslab_kernel_o6(recipe, epi);
+    case 8: return fdw_pslab_kernel_o8(recipe, epi);
     }
     return nullptr;
 }
@@ -558,9 +573,10 @@ static bool tile_plan(const fdw_ctx *c, int nc, int rows, int nbuf, TilePlan *be
         if (t.tr < GUARD) t.tr = GUARD < rows ? GUARD : rows; /* a tile at least as tall as the halo it feeds */
         t.nty = (rows + t.tr - 1) / t.tr;
         if ((long long)t.ntx * t.nty > c->nsm) continue;
-        t.ch = (t.tc4 * t.tr + 511) / 512;
-        t.threads = ((t.tc4 * ((t.tr + t.ch - 1) / t.ch) + 31) / 32) * 32;
-        if (t.threads > 512) continue;
+        const int npts = 4 * t.tc4 * t.tr; /* one point per thread and round */
+        t.ch = (npts + 1023) / 1024;       /* rounds */
+        t.threads = (((npts + t.ch - 1) / t.ch + 31) / 32) * 32;
+        if (t.threads > 1024) t.threads = 1024;
         t.smem = ((size_t)nbuf * (t.tr + 2 * GUARD) * 4 * (t.tc4 + 2)        /* field / velocity tiles */
                   + 4 * (t.tc4 + 2) + 8 + t.tr + 2 * GUARD + 8) * sizeof(float); /* sponge tables */
         if (t.smem > (size_t)c->smem_optin) continue;
@@ -575,7 +591,7 @@ static int tile_launch(fdw_ctx *c, const void *k, TileArgs &ta, const TilePlan &
     ta.tc4 = tp.tc4; ta.tr = tp.tr; ta.ntx = tp.ntx; ta.nty = tp.nty; ta.ch = tp.ch;
     if (const char *e = getenv("FDW_TILE_DBG")) ta.dbg = atoi(e);
     if (getenv("FDW_TILE_VERBOSE"))
-        fprintf(stderr, "fdwave tile plan: %d x %d tiles of %d float4 columns x %d rows, %d rows/thread, %d threads, %zu B smem\n",
+        fprintf(stderr, "fdwave tile plan: %d x %d tiles of %d float4 columns x %d rows, %d point(s)/thread, %d threads, %zu B smem\n",
                 tp.ntx, tp.nty, tp.tc4, tp.tr, tp.ch, tp.threads, tp.smem);
     ta.pa.base.apitch = c->pitch;
     ta.pa.base.pitch = 4LL * (tp.tc4 + 2);
@@ -896,6 +912,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_PERSIST_LIMIT")) c->persist_limit = atoll(e);
     cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, prm->device);
     if (const char *e = getenv("FDW_TILE")) c->use_tile = atoi(e);
+    if (const char *e = getenv("FDW_PSLAB")) c->use_pslab = atoi(e);
+    if (const char *e = getenv("FDW_PSLAB_LIMIT")) c->pslab_limit = atoll(e);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
@@ -2027,11 +2045,74 @@ static int peer_level_pair_graph(fdw_ctx *c, int it)
     return FDW_OK;
 }
 
+/* thin slabs: all nsteps levels in ONE cooperative launch of the persistent slab kernel; 1 = done */
+static int try_pslab(fdw_ctx *c, int it0, int n)
+{
+    if (!c->use_pslab || !c->coop || n < 2 || c->step_open) return 0;
+    const int epi = phase_epi(c->phase);
+    const void *k = pslab_kernel(c->prm.order, c->prm.recipe, epi);
+    if (!k) return 0;
+    StepArgs base;
+    base_args(c, 0, &base);
+    const int rows = base.row1 - base.row0, nc = base.ncol4;
+    if (rows <= 0 || nc <= 0 || (long long)nc * rows >= c->pslab_limit) return 0;
+    const bool source = !c->wavelet.empty() && c->phase != PHASE_RTM_BWD;
+    if (source && (it0 < 0 || (size_t)(it0 + n) > c->wavelet.size() || !c->wavelet_d)) return 0;
+    const bool tap = c->prm.taper != FDW_TAPER_NONE;
+    const int threads = 128;
+    PSlabArgs sa;
+    memset(&sa, 0, sizeof sa);
+    persist_args(c, 0, base, tap, source, it0, n, c->phase == PHASE_RTM_BWD ? 1 : 0,
+                 [&](StepArgs &a) { phase_fill(c, c->phase, it0, a); a.push_nloc = c->nloc; }, &sa.pa);
+    sa.nbx = (nc + threads - 1) / threads;
+    /* boundary rows only where a neighbour exists and inside the updated rows */
+    sa.rows_lo = c->peer[0].on ? GUARD : 0;
+    sa.rows_hi = c->peer[1].on ? GUARD : 0;
+    if (rows < sa.rows_lo + sa.rows_hi || base.row0 != 0 || base.row1 != c->nloc) return 0;
+    const int cap = c->nsm * cached_occupancy(k, threads);
+    const int nbound = sa.nbx * ((sa.rows_lo ? 1 : 0) + (sa.rows_hi ? 1 : 0));
+    const int mid_rows = rows - sa.rows_lo - sa.rows_hi;
+    int chunks = (cap - nbound) / sa.nbx; /* interior row chunks so that every CTA has at most one item per level */
+    if (chunks < 1) return 0;
+    sa.rpc = mid_rows > 0 ? (mid_rows + chunks - 1) / chunks : 1;
+    if (sa.rpc < 2) sa.rpc = 2;
+    sa.nmid = mid_rows > 0 ? (mid_rows + sa.rpc - 1) / sa.rpc : 0;
+    const int nitems = nbound + sa.nbx * sa.nmid;
+    const int grid = nitems < cap ? nitems : cap;
+    /* level l writes the buffer that is "older" at that level: older at entry for even l, newest at entry for odd l */
+    const int wb[2] = {c->older[0], c->newest[0]};
+    for (int par = 0; par < 2; par++) {
+        sa.push_lo[par] = peer_image(c, 0, wb[par]);
+        sa.push_hi[par] = peer_image(c, 1, wb[par]);
+    }
+    sa.pw_flags = c->flags_d;
+    sa.ps_lo = c->peer[0].on ? c->peer[0].flags + 1 : nullptr; /* this slab is the lower neighbour's upper one */
+    sa.ps_hi = c->peer[1].on ? c->peer[1].flags + 0 : nullptr;
+    sa.ps_count = c->pcount_d;
+    sa.pw_err = c->errflag_d;
+    sa.seq0 = c->peer_seq;
+    if (cudaMemsetAsync(c->barrier_d, 0, sizeof(unsigned), c->stream) != cudaSuccess) return 0;
+    void *params[] = {&sa};
+    cudaError_t e = cudaLaunchCooperativeKernel(k, dim3(grid), dim3(threads), params, 0, c->stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    c->launches++;
+    c->pslab_launches++;
+    c->persist_launches++;
+    c->peer_waits++;
+    c->peer_seq += (unsigned)n;
+    replay_bookkeeping(c, n, tap);
+    return 1;
+}
+
 extern "C" int fdw_peer_levels(fdw_ctx *c, int it0, int nsteps)
 {
     if (!c || nsteps < 0) return FDW_ERR_ARG;
     if (!c->peer[0].on && !c->peer[1].on) { fdw_set_error("fdw_peer_levels: no neighbour attached"); return FDW_ERR_STATE; }
     CHECK(bind(c));
+    if (try_pslab(c, it0, nsteps)) return FDW_OK;
     int it = it0;
     const int end = it0 + nsteps;
     if (c->use_graph && nsteps >= 6) {
@@ -2107,6 +2188,7 @@ extern "C" long long fdw_counter(fdw_ctx *c, int which)
     case FDW_COUNTER_GRAPH_REPLAYS: return c->graph_replays;
     case FDW_COUNTER_PERSIST_LAUNCHES: return c->persist_launches;
     case FDW_COUNTER_TILE_LAUNCHES: return c->tile_launches;
+    case FDW_COUNTER_PSLAB_LAUNCHES: return c->pslab_launches;
     }
     return 0;
 }

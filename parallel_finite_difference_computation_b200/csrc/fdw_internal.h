@@ -21,6 +21,10 @@ const void *fdw_tile_kernel_o2(int recipe, int epi); /* epi < 0: GPU-family back
 const void *fdw_tile_kernel_o4(int recipe, int epi);
 const void *fdw_tile_kernel_o6(int recipe, int epi);
 const void *fdw_tile_kernel_o8(int recipe, int epi);
+const void *fdw_pslab_kernel_o2(int recipe, int epi);
+const void *fdw_pslab_kernel_o4(int recipe, int epi);
+const void *fdw_pslab_kernel_o6(int recipe, int epi);
+const void *fdw_pslab_kernel_o8(int recipe, int epi);
 const void *fdw_lap_kernel_o2(void);
 const void *fdw_lap_kernel_o4(void);
 const void *fdw_lap_kernel_o6(void);

@@ -118,8 +118,8 @@ struct Level {
     float *pp;
     const float *vdt; /* fl32(v2*dt2) in the layout of p / pp */
     float *mirror;    /* tile kernel: the global copy of the level being written (null otherwise) */
-    unsigned s_p, s_pp, s_vdt, s_field; /* tile kernel: shared-window byte addresses of the tile copies' origins */
     const float *tz, *tx; /* sponge tables (StepArgs::tz / tx, or the tile kernel's shared-memory copies) */
+    float *push_lo, *push_hi; /* EPI_PUSH targets of this level (StepArgs::push_*; per level in the persistent slab kernel) */
     int np, no;
     int src_on;
     float src_amp;
@@ -132,7 +132,7 @@ struct Level {
 FDW_HD Level level_of(const StepArgs &a)
 {
     Level lv;
-    lv.p = a.p; lv.pp = a.pp; lv.vdt = a.vdt; lv.mirror = nullptr; lv.s_p = lv.s_pp = lv.s_vdt = lv.s_field = 0; lv.tz = a.tz; lv.tx = a.tx; lv.np = a.np; lv.no = a.no; lv.src_on = a.src_on; lv.src_amp = a.src_amp;
+    lv.p = a.p; lv.pp = a.pp; lv.vdt = a.vdt; lv.mirror = nullptr; lv.tz = a.tz; lv.tx = a.tx; lv.push_lo = a.push_lo; lv.push_hi = a.push_hi; lv.np = a.np; lv.no = a.no; lv.src_on = a.src_on; lv.src_amp = a.src_amp;
     lv.rec_it = a.rec_it; lv.inj_tidx = a.inj_tidx; lv.hist_w = a.hist_w; lv.hist_r = a.hist_r;
     lv.img_field = a.img_field;
     return lv;
@@ -166,8 +166,9 @@ FDW_HD Level persist_level_of(const PersistArgs &pa, int l)
     lv.pp = (l & 1) ? pa.bufN : pa.bufO;
     lv.vdt = pa.base.vdt;
     lv.mirror = nullptr;
-    lv.s_p = lv.s_pp = lv.s_vdt = lv.s_field = 0;
+   
     lv.tz = pa.base.tz; lv.tx = pa.base.tx;
+    lv.push_lo = lv.push_hi = nullptr;
     if (!pa.sponge) {
         lv.np = l == 0 ? pa.pendN : 0;
         lv.no = l == 0 ? pa.pendO : (l == 1 ? pa.pendN : 0);
@@ -458,8 +459,8 @@ FDW_HD void row_outputs(const StepArgs &a, const Level &lv, const float4 c4, con
     const long long ap = a.apitch;
     /* ---- halo push: boundary rows go to the neighbour's ghost rows over NVLink */
     if (EPI & EPI_PUSH) {
-        if (a.push_lo && lr < GUARD) st4(a.push_lo + (long long)lr * ap + j0, res);
-        if (a.push_hi && lr >= a.push_nloc - GUARD) st4(a.push_hi + (long long)lr * ap + j0, res);
+        if (lv.push_lo && lr < GUARD) st4(lv.push_lo + (long long)lr * ap + j0, res);
+        if (lv.push_hi && lr >= a.push_nloc - GUARD) st4(lv.push_hi + (long long)lr * ap + j0, res);
     }
     /* ---- seismogram sample: the newer level after one more sponge pass */
     if ((EPI & EPI_RECORD) && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n && a.rec_j >= j0 && a.rec_j < j0 + 4) {
@@ -506,8 +507,8 @@ FDW_HD bool sponge_setup(const StepArgs &a, const float *tz, int j0, float (&zf)
     return zany;
 }
 
-/* where the two time levels and v2*dt2 live: global memory (64-bit byte addresses) or, in the tile kernel,
- * the CTA's shared-memory window (32-bit byte addresses, LDS / STS) */
+/* addresses are handled as 64-bit integers (byte addresses of global memory): the cursor arithmetic of
+ * step_rows then compiles to plain integer adds from uniform registers */
 template <bool TILE> struct Space;
 template <> struct Space<false> {
     typedef unsigned long long addr;
@@ -516,27 +517,9 @@ template <> struct Space<false> {
     static FDW_HDM float4 ld_stream(addr x) { return ld4_stream((const float *)x); }
     static FDW_HDM void st(addr x, float4 v) { st4((float *)x, v); }
 };
-#ifdef __CUDACC__
-template <> struct Space<true> {
-    typedef unsigned addr;
-    typedef int diff;
-    static __device__ __forceinline__ float4 ld(addr x)
-    {
-        float4 v;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(x));
-        return v;
-    }
-    static __device__ __forceinline__ float4 ld_stream(addr x) { return ld(x); }
-    static __device__ __forceinline__ void st(addr x, float4 v)
-    {
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(x), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    }
-};
-#endif
 
-/* rows [rb, re) of the float4 column at j0.  TILE: the levels, v2*dt2 and the imaging operand are the
- * shared-memory tile copies lv.s_* (pitch a.pitch = the tile's); results are stored to the tile and mirrored
- * to the global level lv.mirror. */
+/* rows [rb, re) of the float4 column at j0 (TILE is always false: the small-grid tile kernel has its own
+ * point-per-thread body, fdw_tile_core.h) */
 template <int ORDER, int RECIPE, bool TAPER, int EPI, bool PACKED, bool TILE>
 FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const int rb, const int re)
 {
@@ -564,9 +547,8 @@ FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const in
     /* ONE row cursor per thread (the centre row of the newer level); every other address of a row is the
      * cursor plus a launch-uniform byte delta, which costs an integer add from a uniform register instead
      * of a second and third loop-carried pointer pair (registers are what limits the resident warps). */
-    addr org_p, org_pp, org_v, org_f;
-    if (TILE) { org_p = (addr)lv.s_p; org_pp = (addr)lv.s_pp; org_v = (addr)lv.s_vdt; org_f = (addr)lv.s_field; }
-    else { org_p = (addr)(size_t)lv.p; org_pp = (addr)(size_t)lv.pp; org_v = (addr)(size_t)lv.vdt; org_f = (addr)(size_t)lv.img_field; }
+    const addr org_p = (addr)(size_t)lv.p, org_pp = (addr)(size_t)lv.pp, org_v = (addr)(size_t)lv.vdt,
+               org_f = (addr)(size_t)lv.img_field;
     const diff rowb = (diff)(a.pitch * (long long)sizeof(float));
     const diff d_in = (diff)H * rowb;           /* centre row -> incoming row */
     const diff d_pp = (diff)(org_pp - org_p);   /* -> older level, same point */
@@ -613,7 +595,6 @@ FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const in
                 w[(u + 2 * H) % W] = wn;
                 const float4 res = row_update<ORDER, RECIPE, EPI, PACKED>(a, lv, w, u, l4, r4, o4, v4, gi, j0, ring, near_src);
                 S::st(ppc, res);
-                if (TILE) st4(lv.mirror + (long long)lr * a.apitch + j0, res);
                 if (EPI) {
                     float4 f4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n)
@@ -648,6 +629,25 @@ struct TileArgs {
     float *sav0, *sav1;
     unsigned *flags; /* one "levels completed" word per tile, 128 B apart, zeroed before the launch */
     int dbg; /* 8: device-wide counter barrier instead of neighbour flags.  Timing experiments only (FDW_TILE_DBG; results are wrong when set): 1 no barrier, 2 no update, 4 no ring load */
+};
+
+/* arguments of the persistent slab kernel (thin slabs of a slab-decomposed run: a level is tens of microseconds,
+ * so the per-level launches -- even replayed as a CUDA graph -- cost as much as the arithmetic): ONE cooperative
+ * launch runs nlevels levels of the slab; per level the CTAs that own boundary rows first wait for the
+ * neighbours' flags, update their rows and store them into the neighbours' ghost rows over NVLink (EPI_PUSH), the
+ * last of them raises this slab's flag there; the other CTAs update the interior meanwhile; a device-wide barrier
+ * closes the level. */
+struct PSlabArgs {
+    PersistArgs pa;          /* pa.base: the whole slab (col4_0..ncol4, row0..row1), EPI_PUSH bookkeeping fields unused */
+    float *push_lo[2], *push_hi[2]; /* the neighbours' copies of the buffer written at even / odd levels (null: grid edge) */
+    const unsigned *pw_flags; /* this slab's flag block (written by the neighbours) */
+    unsigned *ps_lo, *ps_hi, *ps_count;
+    int *pw_err;
+    unsigned seq0;           /* flag value the neighbours reach before level 0 of this launch */
+    int nbx;                 /* item columns (blockDim float4 columns each) */
+    int rows_lo, rows_hi;    /* boundary rows with a neighbour below / above (0 or GUARD) */
+    int rpc;                 /* rows per interior item */
+    int nmid;                /* interior row chunks */
 };
 
 /* stand-alone Laplacian (config 1; kernel_lap fd-source-code.cu:110-135): the

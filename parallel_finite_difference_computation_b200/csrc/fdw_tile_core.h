@@ -8,9 +8,13 @@
  * CTA per tile, all CTAs co-resident (cooperative launch), and each CTA keeps ITS tile of both time
  * levels and of v2*dt2 in shared memory for the whole phase:
  *
- *   per level   update own points from shared memory (the same step_rows body as every other kernel:
- *               identical arithmetic, sponge-on-load, source, epilogues), storing each result into the
- *               tile AND into the global copy of the level (lv.mirror: fire-and-forget, L2)
+ *   per level   update own points from shared memory, ONE POINT PER THREAD (tile_point): with a few hundred
+ *               points per SM the level is a latency chain, not a throughput problem -- the float4-column
+ *               body of the big-grid kernels (one warp = ~700 dependent-ish instructions per level, measured
+ *               2.7 us) is replaced by ~100 instructions per thread over 4x as many threads; the per-point
+ *               operation sequence (recipe, sponge on load, source, epilogues) is the same, hence the same
+ *               bits.  Each result goes into the tile AND into the global copy of the level (lv.mirror:
+ *               fire-and-forget, L2)
  *               -> release/acquire counter barrier (measured on B200: 1.3 us for 148 CTAs,
  *                  profiles/r02a_kbench_sync_latencies.log)
  *               -> fetch only the halo ring (4 rows above/below, one float4 column left/right) of the
@@ -148,12 +152,6 @@ __device__ __forceinline__ float *tile_origin(float *buf, const TileGeom &g)
 {
     return buf + (long long)(GUARD - g.r0) * g.sp + (4 - 4 * g.c0);
 }
-/* the same as a byte address in the shared-memory window (wraps modulo 2^32 like the kernel's 32-bit cursor) */
-__device__ __forceinline__ unsigned tile_origin_s(float *buf, const TileGeom &g)
-{
-    return (unsigned)__cvta_generic_to_shared(buf) + 4u * (unsigned)((GUARD - g.r0) * g.sp + (4 - 4 * g.c0));
-}
-
 /* whole tile incl. halo ring <- global level (rows r0-GUARD .. r1+GUARD, float4 columns c0-1 .. c1) */
 __device__ __forceinline__ void tile_load_all(float *buf, const float *glob, long long gpitch, const TileGeom &g)
 {
@@ -203,15 +201,156 @@ __device__ __forceinline__ void tile_load_tables(float *stz, float *stx, const S
     for (int e = threadIdx.x; e < nx; e += blockDim.x) stx[e] = a.tx[g.r0 - GUARD + e];
 }
 
-/* this thread's float4 column and rows inside the tile; false = idle thread */
-__device__ __forceinline__ bool tile_my_rows(const TileArgs &ta, const TileGeom &g, int *j0, int *rb, int *re)
+/* ---- one point.  Tile buffers are addressed through "origins" in the shared-memory window (32-bit byte
+ * addresses, LDS / STS; arithmetic wraps modulo 2^32): org + 4 * (r * sp + j) is (global row r, column j). */
+struct TilePt {
+    unsigned n;   /* newer level (stencil input) */
+    unsigned o;   /* older level in, new level out */
+    unsigned v;   /* fl32(v2*dt2) */
+    unsigned f;   /* EPI_IMG_FIELD: reconstructed source level */
+    unsigned tz, tx; /* sponge tables: tz + 4*j, tx + 4*row */
+    int sp;
+};
+
+__device__ __forceinline__ float lds(unsigned addr)
 {
-    const int col = threadIdx.x % ta.tc4, chunk = threadIdx.x / ta.tc4;
-    const int q = g.c0 + col;
-    *j0 = 4 * q;
-    *rb = g.r0 + chunk * ta.ch;
-    *re = *rb + ta.ch < g.r1 ? *rb + ta.ch : g.r1;
-    return q < g.c1 && *rb < g.r1;
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts(unsigned addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ unsigned tile_origin_s(const float *buf, const TileGeom &g)
+{
+    return (unsigned)__cvta_generic_to_shared(buf) + 4u * (unsigned)((GUARD - g.r0) * g.sp + (4 - 4 * g.c0));
+}
+
+/* sponge applied cnt times to one value at (row gi, column j): (v*Z)*X per application (kernel_tapper
+ * fd-code.cu:94-117, taper_apply taper.c:47-67), Z only on rows the reference's launch covered (tz_ilim),
+ * X only on the columns it applies to (tx_jlim) */
+/* (a real call on purpose: the rare path must not bloat the instruction footprint of the level loop) */
+static __device__ __noinline__ float tile_tap(const StepArgs &a, const TilePt &t, float v, int gi, int j, int cnt)
+{
+    const float zf = gi < a.tz_ilim ? lds(t.tz + 4u * (unsigned)j) : 1.0f;
+    const float xf = j < a.tx_jlim ? lds(t.tx + 4u * (unsigned)gi) : 1.0f;
+    for (int c = 0; c < cnt; c++) v = fmul(fmul(v, zf), xf);
+    return v;
+}
+
+template <int ORDER, int RECIPE, bool TAPER, int EPI>
+__device__ __forceinline__ void tile_point(const StepArgs &a, const Level &lv, const TilePt &t, const int gi, const int j)
+{
+    constexpr int H = ORDER / 2;
+    const unsigned off = 4u * (unsigned)(gi * t.sp + j), rowb = 4u * (unsigned)t.sp;
+    const unsigned ctr = t.n + off;
+    float z[2 * H + 1], x[2 * H + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * H; k++) z[k] = lds(ctr + 4u * (unsigned)(k - H));
+#pragma unroll
+    for (int k = 0; k <= 2 * H; k++)
+        if (k != H) x[k] = lds(ctr + (unsigned)(k - H) * rowb);
+    float o = lds(t.o + off);
+    const float v = lds(t.v + off);
+    /* sponge on load; all factors are exactly 1 away from the sponge (StepArgs::tap_*), where nothing is done */
+    if (TAPER && (lv.np | lv.no) &&
+        (j - H < a.tap_jlo || j + H >= a.tap_jhi || gi - H < a.tap_ilo || gi + H >= a.tap_ihi)) {
+#pragma unroll
+        for (int k = 0; k <= 2 * H; k++) z[k] = tile_tap(a, t, z[k], gi, j + k - H, lv.np);
+#pragma unroll
+        for (int k = 0; k <= 2 * H; k++)
+            if (k != H) x[k] = tile_tap(a, t, x[k], gi + k - H, j, lv.np);
+        o = tile_tap(a, t, o, gi, j, lv.no);
+    }
+    x[H] = z[H];
+    const float cc = z[H];
+    float lap;
+    if (RECIPE == RECIPE_G) { /* fd-code.cu:66-72 (the leading "0 +" dropped as in row_update) */
+        float az = fmul(z[0], a.cz[0]), ax = fmul(x[0], a.cx[0]);
+#pragma unroll
+        for (int io = 1; io <= ORDER; io++) {
+            az = fadd(az, fmul(z[io], a.cz[io]));
+            ax = fadd(ax, fmul(x[io], a.cx[io]));
+        }
+        lap = fadd(az, ax);
+    } else if (RECIPE == RECIPE_C) { /* fd.c:30-33 */
+        float acm = fmul(fmul(z[0], a.cz[0]), a.dz2inv);
+        acm = fadd(acm, fmul(fmul(x[0], a.cx[0]), a.dx2inv));
+#pragma unroll
+        for (int io = 1; io <= ORDER; io++) {
+            acm = fadd(acm, fmul(fmul(z[io], a.cz[io]), a.dz2inv));
+            acm = fadd(acm, fmul(fmul(x[io], a.cx[io]), a.dx2inv));
+        }
+        lap = acm;
+    } else {
+        float sm = fmul(cc, a.cz[H] + a.cx[H]);
+#pragma unroll
+        for (int d = 1; d <= H; d++) {
+            sm = ffma(a.cz[H + d], z[H - d] + z[H + d], sm);
+            sm = ffma(a.cx[H + d], x[H - d] + x[H + d], sm);
+        }
+        lap = sm;
+    }
+    if (gi < a.lap_i0 || gi >= a.lap_i1 || j < a.lap_j0 || j >= a.lap_j1) lap = 0.0f; /* ring (quirk Q2 read as 0) */
+    float res = RECIPE == RECIPE_FAST ? ffma(v, lap, 2.0f * cc - o) : leap(cc, o, fmul(v, lap));
+    /* ---- source */
+    if (lv.src_on) {
+        const int di = gi - a.src_gi, dj = j - a.src_j;
+        if (di >= -a.src_rad && di <= a.src_rad && dj >= -a.src_rad && dj <= a.src_rad && j < a.nze)
+            res = fadd(res, a.src_rad ? fmul(lv.src_amp, a.src_w[(di + 3) * 7 + (dj + 3)]) : lv.src_amp);
+    }
+    /* ---- receiver back-injection */
+    if ((EPI & EPI_INJECT) && j == a.inj_j && gi >= a.inj_gi0 && gi < a.inj_gi0 + a.inj_n) {
+        const long long idx = a.dobs_base + (long long)(gi - a.inj_gi0) * a.inj_nt + lv.inj_tidx;
+        res = fadd(res, (idx >= 0 && idx < a.dobs_len) ? a.dobs[idx] : 0.0f);
+    }
+    sts(t.o + off, res);
+    lv.mirror[(long long)gi * a.apitch + j] = res;
+    /* ---- side outputs (global memory, pitch a.apitch) */
+    if ((EPI & EPI_RECORD) && j == a.rec_j && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n)
+        a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = TAPER ? tile_tap(a, t, cc, gi, j, 1) : cc;
+    if ((EPI & EPI_HSTORE) && gi >= a.hist_gi0 && gi < a.hist_gi0 + a.hist_n)
+        lv.hist_w[(long long)(gi - a.hist_gi0) * a.apitch + j] = cc;
+    if ((EPI & EPI_IMG_HIST) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
+        float *ip = a.img + (long long)(gi - a.img_gi0) * a.apitch + j;
+        *ip = fadd(*ip, fmul(lv.hist_r[(long long)(gi - a.hist_gi0) * a.apitch + j], cc));
+    }
+    if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
+        float *ip = a.img + (long long)(gi - a.img_gi0) * a.apitch + j;
+        *ip = fadd(*ip, fmul(lds(t.f + off), res));
+    }
+}
+
+/* the points of the tile this thread owns: one per round (point index = thread + round * blockDim); the first
+ * rounds' coordinates are worked out once, outside the level loop (an integer division per point otherwise) */
+struct TileWork {
+    enum { KEEP = 2 };
+    int npts, w, r0, j00;
+    int gi[KEEP], j[KEEP];
+};
+
+__device__ __forceinline__ TileWork tile_work(const TileGeom &g)
+{
+    TileWork k;
+    k.w = 4 * (g.c1 - g.c0); k.npts = k.w * (g.r1 - g.r0); k.r0 = g.r0; k.j00 = 4 * g.c0;
+#pragma unroll
+    for (int r = 0; r < TileWork::KEEP; r++) {
+        const int p = threadIdx.x + r * blockDim.x;
+        k.gi[r] = g.r0 + p / k.w;
+        k.j[r] = 4 * g.c0 + p % k.w;
+    }
+    return k;
+}
+
+template <int ORDER, int RECIPE, bool TAPER, int EPI>
+__device__ __forceinline__ void tile_update(const StepArgs &a, const Level &lv, const TilePt &t, const TileWork &k)
+{
+#pragma unroll
+    for (int r = 0; r < TileWork::KEEP; r++)
+        if ((int)(threadIdx.x + r * blockDim.x) < k.npts) tile_point<ORDER, RECIPE, TAPER, EPI>(a, lv, t, k.gi[r], k.j[r]);
+    for (int p = threadIdx.x + TileWork::KEEP * blockDim.x; p < k.npts; p += blockDim.x)
+        tile_point<ORDER, RECIPE, TAPER, EPI>(a, lv, t, k.r0 + p / k.w, k.j00 + p % k.w);
 }
 
 /* forward phases: nlevels levels of pair 0 (plain, modelling, rtm forward with history, rtm backward) */
@@ -231,19 +370,20 @@ __device__ __forceinline__ void tile_forward(const TileArgs &ta, float *smem)
     tile_load_all(sbuf[1], pa.bufO, a.apitch, g);
     tile_load_all(sv, a.vdt, a.apitch, g);
     __syncthreads();
-    int j0, rb, re;
-    const bool active = tile_my_rows(ta, g, &j0, &rb, &re);
     const unsigned nblk = gridDim.x;
+    const TileWork work = tile_work(g);
+    const unsigned org[2] = {tile_origin_s(sbuf[0], g), tile_origin_s(sbuf[1], g)};
+    TilePt t;
+    t.v = tile_origin_s(sv, g); t.f = 0; t.sp = g.sp;
+    t.tz = (unsigned)__cvta_generic_to_shared(stz) - 4u * (unsigned)(4 * g.c0 - 4);
+    t.tx = (unsigned)__cvta_generic_to_shared(stx) - 4u * (unsigned)(g.r0 - GUARD);
     for (int l = 0; l < pa.nlevels; l++) {
         Level lv = persist_level_of(pa, l);
         float *gnew = lv.pp; /* global copy of the level being written */
-        lv.s_p = tile_origin_s(sbuf[l & 1], g);
-        lv.s_pp = tile_origin_s(sbuf[(l & 1) ^ 1], g);
-        lv.s_vdt = tile_origin_s(sv, g);
         lv.mirror = gnew;
-        lv.tz = stz - (4 * g.c0 - 4);
-        lv.tx = stx - (g.r0 - GUARD);
-        if (active && !(ta.dbg & 2)) step_rows<ORDER, RECIPE, true, EPI, true, true>(a, lv, j0, rb, re);
+        t.n = org[l & 1];
+        t.o = org[(l & 1) ^ 1];
+        if (!(ta.dbg & 2)) tile_update<ORDER, RECIPE, true, EPI>(a, lv, t, work);
         if (l + 1 == pa.nlevels) break; /* the kernel boundary orders the last level */
         if (!(ta.dbg & 1) && !tile_sync(ta, (unsigned)(l + 1), nblk, &lost)) return;
         if (!(ta.dbg & 4)) tile_load_ring(sbuf[(l & 1) ^ 1], gnew, a.apitch, g);
@@ -276,38 +416,38 @@ __device__ __forceinline__ void tile_backward(const TileArgs &ta, float *smem)
     tile_load_all(sr[1], pa.bufO, a.apitch, g);
     tile_load_all(sv, a.vdt, a.apitch, g);
     __syncthreads();
-    int j0, rb, re;
-    const bool active = tile_my_rows(ta, g, &j0, &rb, &re);
     const unsigned nblk = gridDim.x;
+    const TileWork work = tile_work(g);
+    const unsigned os[2] = {tile_origin_s(ss[0], g), tile_origin_s(ss[1], g)};
+    const unsigned orr[2] = {tile_origin_s(sr[0], g), tile_origin_s(sr[1], g)};
+    TilePt t;
+    t.v = tile_origin_s(sv, g); t.f = 0; t.sp = g.sp;
+    t.tz = (unsigned)__cvta_generic_to_shared(stz) - 4u * (unsigned)(4 * g.c0 - 4);
+    t.tx = (unsigned)__cvta_generic_to_shared(stx) - 4u * (unsigned)(g.r0 - GUARD);
     for (int it = 0; it < pa.nlevels; it++) {
         /* ---- source field: cur = index of the level the imaging condition uses at this step */
         int cur = it & 1; /* it = 0: u(T) in ss[0]; it = 1: u(T-1) in ss[1]; then the update writes ss[it & 1] */
         if (it >= 2) {
             Level ls;
-            ls.p = nullptr; ls.pp = nullptr; ls.vdt = nullptr;
-            ls.s_p = tile_origin_s(ss[(it & 1) ^ 1], g); /* prev1 */
-            ls.s_pp = tile_origin_s(ss[it & 1], g);      /* prev2, overwritten */
-            ls.s_vdt = tile_origin_s(sv, g);
-            ls.s_field = 0;
-            ls.tz = stz - (4 * g.c0 - 4);
-            ls.tx = stx - (g.r0 - GUARD);
+            ls.p = nullptr; ls.pp = nullptr; ls.vdt = nullptr; ls.tz = nullptr; ls.tx = nullptr;
             ls.mirror = gs[it & 1];
             ls.np = ls.no = 0; ls.src_on = 0; ls.src_amp = 0.0f; ls.rec_it = 0; ls.inj_tidx = 0;
             ls.hist_w = nullptr; ls.hist_r = nullptr; ls.img_field = nullptr;
-            if (active) step_rows<ORDER, RECIPE, false, 0, true, true>(a, ls, j0, rb, re);
+            t.n = os[(it & 1) ^ 1]; /* prev1 */
+            t.o = os[it & 1];       /* prev2, overwritten */
+            tile_update<ORDER, RECIPE, false, 0>(a, ls, t, work);
+            /* no barrier: the imaging below reads this level only at the thread's own points (same point-to-thread
+             * mapping in both updates) */
         }
         /* ---- receiver field */
         Level lv = persist_level_of(pa, it);
         float *gnew = lv.pp;
-        lv.s_p = tile_origin_s(sr[it & 1], g);
-        lv.s_pp = tile_origin_s(sr[(it & 1) ^ 1], g);
-        lv.s_vdt = tile_origin_s(sv, g);
         lv.mirror = gnew;
-        lv.tz = stz - (4 * g.c0 - 4);
-        lv.tx = stx - (g.r0 - GUARD);
         lv.src_on = 0;
-        lv.s_field = tile_origin_s(ss[cur], g);
-        if (active) step_rows<ORDER, RECIPE, true, EPI_INJECT | EPI_IMG_FIELD, true, true>(a, lv, j0, rb, re);
+        t.n = orr[it & 1];
+        t.o = orr[(it & 1) ^ 1];
+        t.f = os[cur];
+        tile_update<ORDER, RECIPE, true, EPI_INJECT | EPI_IMG_FIELD>(a, lv, t, work);
         if (it + 1 == pa.nlevels) break;
         if (!tile_sync(ta, (unsigned)(it + 1), nblk, &lost)) return;
         if (it >= 2) tile_load_ring(ss[it & 1], gs[it & 1], a.apitch, g);

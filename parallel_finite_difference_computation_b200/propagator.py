@@ -193,6 +193,9 @@ class Wave2D:
     def tile_launches(self):
         return self.L.fdw_counter(self.h, _lib.COUNTER_TILE_LAUNCHES)
 
+    def pslab_launches(self):
+        return self.L.fdw_counter(self.h, _lib.COUNTER_PSLAB_LAUNCHES)
+
     def shot_phase_device(self, phase, sx, sz, gz, dobs_all=None, is_=0):
         """one phase of a CPU-family shot left on the device (fdw_shot_begin + fdw_shot_run, asynchronous):
         bracket with mark_begin()/mark_end() for the device time of the phase's level loop"""

@@ -71,7 +71,7 @@ def main():
         dist.all_gather_object(parts, (na, nb_))
         results[halo] = parts
         if halo == "p2p":
-            graph_replays = sp.w.graph_replays()
+            graph_replays = (sp.w.graph_replays(), sp.w.pslab_launches())
         sp.close()
     ok = True
     if rank == 0:
@@ -88,7 +88,8 @@ def main():
                 np.array_equal(older.view(np.uint32), b.view(np.uint32))
             print("slab x%d halo=%s vs single domain bitwise: %s" % (world, halo, "OK" if good else "MISMATCH"), flush=True)
             ok = ok and good
-        print("graph replays on rank 0: %s" % graph_replays, flush=True)
+        print("graph replays on rank 0: %s" % graph_replays[0], flush=True)
+        print("persistent slab launches on rank 0: %s" % graph_replays[1], flush=True)
     for halo in HALOS:
         ok = check_domain_divided_cpu_family(rank, world, lrank, halo) and ok
     ok = check_shot_parallel(rank, world, lrank) and ok

@@ -30,12 +30,19 @@ def _run(port, env_extra, expect):
 def test_slab_and_shot_partitioning_bitwise():
     import torch
 
-    out = _run(29543, {"FDW_SAME_DEVICE": "1"},
-               ("halo=p2p vs single domain bitwise: OK", "mod_main+rtm_main x2 halo=p2p vs one GPU bitwise: OK",
-                "chained stack vs sequential bitwise: OK", "device stack chained vs sequential bitwise: OK"))
-    # the CUDA-graph replay of the level loop really ran
-    line = [ln for ln in out.splitlines() if ln.startswith("graph replays on rank 0:")][0]
-    assert int(line.split(":")[1]) > 0, line
+    expect = ("halo=p2p vs single domain bitwise: OK", "mod_main+rtm_main x2 halo=p2p vs one GPU bitwise: OK",
+              "chained stack vs sequential bitwise: OK", "device stack chained vs sequential bitwise: OK")
+
+    def counter(out, what):
+        line = [ln for ln in out.splitlines() if ln.startswith(what)][0]
+        return int(line.split(":")[1])
+
+    # thin slabs: the whole level loop is ONE launch of the persistent slab kernel (in-kernel acquire / push / release)
+    out = _run(29543, {"FDW_SAME_DEVICE": "1"}, expect)
+    assert counter(out, "persistent slab launches on rank 0:") > 0
+    # the same job through the per-level launches replayed as a CUDA graph (what large slabs use)
+    out = _run(29545, {"FDW_SAME_DEVICE": "1", "FDW_PSLAB": "0"}, expect)
+    assert counter(out, "graph replays on rank 0:") > 0
     if torch.cuda.device_count() >= 2:  # one process per GPU over NVLink, NCCL rendezvous, both halo transports
         _run(29541, {}, ("halo=p2p vs single domain bitwise: OK", "halo=nccl vs single domain bitwise: OK",
                          "mod_main+rtm_main x2 halo=p2p vs one GPU bitwise: OK",
