@@ -117,6 +117,8 @@ struct fdw_ctx {
     long long small_grid_limit = 1LL << 18, fork_limit = 1LL << 20; /* in float4 columns x rows */
     float *wavelet_d = nullptr; /* device copy of the wavelet (persistent kernel) */
     unsigned *barrier_d = nullptr;
+    unsigned long long *ll_d = nullptr;  /* {value, tag} planes of the tile kernels' flag-in-data halo exchange (4 planes) */
+    int use_ll = 1;                      /* FDW_TILE_LL=0: neighbour flags + ring loads instead */
     unsigned *tileflags_d = nullptr; /* neighbour flags of the tile kernels: FDW_TILE_FLAG_WORDS words */
     int *errflag_d = nullptr;
     int coop = 0;                      /* device supports cooperative launches */
@@ -557,7 +559,7 @@ static void replay_bookkeeping(fdw_ctx *c, int n, bool tap, int pair = 0)
  * The grid (nc float4 columns x rows) is cut into at most one tile per SM; among the cuts that fit, the
  * one with the least work per CTA -- own points plus the halo ring it re-reads every level -- wins. */
 enum { FDW_TILE_FLAG_WORDS = 32 * 1024 }; /* 32 words (128 B) per tile */
-struct TilePlan { int tc4, tr, ntx, nty, ch, threads; size_t smem; };
+struct TilePlan { int tc4, tr, ntx, nty, ch, threads, sp; size_t smem; };
 
 static bool tile_plan(const fdw_ctx *c, int nc, int rows, int nbuf, TilePlan *best)
 {
@@ -577,8 +579,11 @@ static bool tile_plan(const fdw_ctx *c, int nc, int rows, int nbuf, TilePlan *be
         t.ch = (npts + 1023) / 1024;       /* rounds */
         t.threads = (((npts + t.ch - 1) / t.ch + 31) / 32) * 32;
         if (t.threads > 1024) t.threads = 1024;
-        t.smem = ((size_t)nbuf * (t.tr + 2 * GUARD) * 4 * (t.tc4 + 2)        /* field / velocity tiles */
-                  + 4 * (t.tc4 + 2) + 8 + t.tr + 2 * GUARD + 8) * sizeof(float); /* sponge tables */
+        /* row pitch: room for one float4 of halo on each side and = tile width modulo 32, so that a warp whose
+         * lanes run on from one tile row into the next still hits 32 different banks */
+        t.sp = 4 * t.tc4 + 32;
+        t.smem = ((size_t)nbuf * (t.tr + 2 * GUARD) * t.sp                    /* field / velocity tiles */
+                  + t.sp + 8 + t.tr + 2 * GUARD + 8) * sizeof(float);         /* sponge tables */
         if (t.smem > (size_t)c->smem_optin) continue;
         const long long cost = (long long)t.tc4 * t.tr + 2LL * GUARD * t.tc4 + 2LL * t.tr;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; *best = t; }
@@ -588,13 +593,22 @@ static bool tile_plan(const fdw_ctx *c, int nc, int rows, int nbuf, TilePlan *be
 
 static int tile_launch(fdw_ctx *c, const void *k, TileArgs &ta, const TilePlan &tp)
 {
-    ta.tc4 = tp.tc4; ta.tr = tp.tr; ta.ntx = tp.ntx; ta.nty = tp.nty; ta.ch = tp.ch;
+    ta.tc4 = tp.tc4; ta.tr = tp.tr; ta.ntx = tp.ntx; ta.nty = tp.nty; ta.ch = tp.ch; ta.sp = tp.sp;
+    if (c->use_ll) {
+        const size_t plane = c->field_elems, bytes = 4 * plane * sizeof(unsigned long long);
+        if (!c->ll_d && cudaMalloc(&c->ll_d, bytes) != cudaSuccess) { (void)cudaGetLastError(); c->ll_d = nullptr; }
+        if (c->ll_d) {
+            if (cudaMemsetAsync(c->ll_d, 0, bytes, c->stream) != cudaSuccess) return 0;
+            ta.ll = c->ll_d + (size_t)(GUARD + 1) * c->pitch; /* local row 0, column 0 of plane 0 */
+            ta.ll_plane = (long long)plane;
+        }
+    }
     if (const char *e = getenv("FDW_TILE_DBG")) ta.dbg = atoi(e);
     if (getenv("FDW_TILE_VERBOSE"))
         fprintf(stderr, "fdwave tile plan: %d x %d tiles of %d float4 columns x %d rows, %d point(s)/thread, %d threads, %zu B smem\n",
                 tp.ntx, tp.nty, tp.tc4, tp.tr, tp.ch, tp.threads, tp.smem);
     ta.pa.base.apitch = c->pitch;
-    ta.pa.base.pitch = 4LL * (tp.tc4 + 2);
+    ta.pa.base.pitch = tp.sp;
     if (tp.smem > 48 * 1024 &&
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -912,6 +926,7 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_PERSIST_LIMIT")) c->persist_limit = atoll(e);
     cudaDeviceGetAttribute(&c->coop, cudaDevAttrCooperativeLaunch, prm->device);
     if (const char *e = getenv("FDW_TILE")) c->use_tile = atoi(e);
+    if (const char *e = getenv("FDW_TILE_LL")) c->use_ll = atoi(e);
     if (const char *e = getenv("FDW_PSLAB")) c->use_pslab = atoi(e);
     if (const char *e = getenv("FDW_PSLAB_LIMIT")) c->pslab_limit = atoll(e);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, prm->device);
@@ -1024,7 +1039,7 @@ extern "C" void fdw_destroy(fdw_ctx *c)
     if (c->ev_staged) cudaEventDestroy(c->ev_staged);
     if (c->ev_shot_done) cudaEventDestroy(c->ev_shot_done);
     cudaFree(c->hist); cudaFree(c->img); cudaFree(c->dobs_d); cudaFree(c->rec_d);
-    cudaFree(c->wavelet_d); cudaFree(c->barrier_d); cudaFree(c->errflag_d); cudaFree(c->tileflags_d);
+    cudaFree(c->wavelet_d); cudaFree(c->barrier_d); cudaFree(c->errflag_d); cudaFree(c->tileflags_d); cudaFree(c->ll_d);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);

@@ -157,6 +157,21 @@ struct PersistArgs {
     unsigned long long timeout_ns; /* device-wide waits give up after this wall time */
 };
 
+/* sponge multiplications pending on the newer / older level at launch-relative level l, in closed form
+ * (the host bookkeeping of step_pair, unrolled) */
+FDW_HD int persist_np(const PersistArgs &pa, int l)
+{
+    if (!pa.sponge) return l == 0 ? pa.pendN : 0;
+    if (pa.sponge_first) return l == 0 ? pa.pendN + 1 : 1;
+    return l == 0 ? pa.pendN : 1;
+}
+FDW_HD int persist_no(const PersistArgs &pa, int l)
+{
+    if (!pa.sponge) return l == 0 ? pa.pendO : (l == 1 ? pa.pendN : 0);
+    if (pa.sponge_first) return l == 0 ? pa.pendO + 1 : (l == 1 ? pa.pendN + 2 : 2);
+    return l == 0 ? pa.pendO : (l == 1 ? pa.pendN + 1 : 2);
+}
+
 /* the Level of launch-relative level l, in closed form (see the host bookkeeping in step_pair) */
 FDW_HD Level persist_level_of(const PersistArgs &pa, int l)
 {
@@ -169,16 +184,8 @@ FDW_HD Level persist_level_of(const PersistArgs &pa, int l)
    
     lv.tz = pa.base.tz; lv.tx = pa.base.tx;
     lv.push_lo = lv.push_hi = nullptr;
-    if (!pa.sponge) {
-        lv.np = l == 0 ? pa.pendN : 0;
-        lv.no = l == 0 ? pa.pendO : (l == 1 ? pa.pendN : 0);
-    } else if (pa.sponge_first) {
-        lv.np = l == 0 ? pa.pendN + 1 : 1;
-        lv.no = l == 0 ? pa.pendO + 1 : (l == 1 ? pa.pendN + 2 : 2);
-    } else {
-        lv.np = l == 0 ? pa.pendN : 1;
-        lv.no = l == 0 ? pa.pendO : (l == 1 ? pa.pendN + 1 : 2);
-    }
+    lv.np = persist_np(pa, l);
+    lv.no = persist_no(pa, l);
     lv.src_on = pa.source;
     lv.src_amp = pa.source ? pa.wavelet[it] : 0.0f;
     lv.rec_it = it;
@@ -513,9 +520,24 @@ template <bool TILE> struct Space;
 template <> struct Space<false> {
     typedef unsigned long long addr;
     typedef long long diff;
+#if defined(__CUDA_ARCH__) && defined(FDW_LDG_ASM)
+    /* trial (tools/kbench5 -DFDW_LDG_ASM): explicit ld.global / st.global instead of the generic LD / ST the
+     * integer-address formulation compiles to */
+    static FDW_HDM float4 ld(addr x)
+    {
+        float4 v;
+        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(x));
+        return v;
+    }
+    static FDW_HDM void st(addr x, float4 v)
+    {
+        asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(x), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+#else
     static FDW_HDM float4 ld(addr x) { return ld4((const float *)x); }
-    static FDW_HDM float4 ld_stream(addr x) { return ld4_stream((const float *)x); }
     static FDW_HDM void st(addr x, float4 v) { st4((float *)x, v); }
+#endif
+    static FDW_HDM float4 ld_stream(addr x) { return ld4_stream((const float *)x); }
 };
 
 /* rows [rb, re) of the float4 column at j0 (TILE is always false: the small-grid tile kernel has its own
@@ -628,6 +650,11 @@ struct TileArgs {
     /* GPU-family backward (k_tile_back): the two saved levels of the source field, u(T) and u(T-1) */
     float *sav0, *sav1;
     unsigned *flags; /* one "levels completed" word per tile, 128 B apart, zeroed before the launch */
+    /* flag-in-data halo exchange (fdw_tile_core.h): planes of {value, level tag} pairs in the global field layout,
+     * two per field (level parity), zeroed before the launch; null = neighbour flags + plain ring loads */
+    unsigned long long *ll;
+    long long ll_plane; /* pairs per plane */
+    int sp;             /* shared-memory row pitch of the tiles in floats */
     int dbg; /* 8: device-wide counter barrier instead of neighbour flags.  Timing experiments only (FDW_TILE_DBG; results are wrong when set): 1 no barrier, 2 no update, 4 no ring load */
 };
 

@@ -14,11 +14,22 @@
  *               2.7 us) is replaced by ~100 instructions per thread over 4x as many threads; the per-point
  *               operation sequence (recipe, sponge on load, source, epilogues) is the same, hence the same
  *               bits.  Each result goes into the tile AND into the global copy of the level (lv.mirror:
- *               fire-and-forget, L2)
- *               -> release/acquire counter barrier (measured on B200: 1.3 us for 148 CTAs,
- *                  profiles/r02a_kbench_sync_latencies.log)
- *               -> fetch only the halo ring (4 rows above/below, one float4 column left/right) of the
- *                  new level from L2 (ld.global.cg: other SMs wrote it) into the tile.
+ *               fire-and-forget, L2).  The sponge is applied where a value ENTERS a tile buffer (own result,
+ *               halo ring, initial load) instead of at each of its 17 uses: the tile is private to its CTA,
+ *               so "sponge on load" degenerates to "sponge once" -- same multiplications in the same order
+ *               (position-only factors), and the tiles that touch the sponge no longer set the pace
+ *               (measured: 3.9 us of a 5.8 us level were the sponge tiles' 19 taps per point)
+ *               -> FLAG-IN-DATA halo exchange: every result is also stored as one 8-byte {value, level tag}
+ *                  pair into a global plane (aligned 8-byte stores are single transactions); a tile's threads
+ *                  poll the pairs of their halo ring (4 points deep, no corners: cross stencil) until the tag
+ *                  is the level they need and copy the value into the tile.  No flag, no fence, no barrier
+ *                  between SMs: the data is its own "ready" signal, one store->L2->load trip per level
+ *                  instead of store, release flag, poll, ring load (measured: 1.9 us -> see DESIGN.md).
+ *                  Two planes per field alternate with the level parity: a tile can be at most one level
+ *                  ahead of its neighbour (it needs the neighbour's previous level to advance), so a pair is
+ *                  never overwritten before it was read.
+ *                  (ta.ll == null keeps the earlier protocol: neighbour flags, measured 1.1 us against 1.4 us
+ *                  for a counter barrier -- profiles/r02a_kbench_sync_latencies.log -- then ring loads.)
  *
  * The global copies stay complete at every level, so everything outside the kernel (exports, history,
  * images, the host bookkeeping of pending sponge counts) is unchanged.  The GPU family's backward pass
@@ -129,7 +140,7 @@ __device__ __forceinline__ bool tile_sync(const TileArgs &ta, unsigned level, un
 
 struct TileGeom {
     int c0, c1, r0, r1; /* owned float4 columns [c0,c1) and rows [r0,r1) */
-    int sp;             /* shared-memory pitch in floats = 4 * (tc4 + 2) */
+    int sp;             /* shared-memory pitch in floats: >= 4 * (tc4 + 2), = tile width mod 32 (conflict-free) */
     int srows;          /* rows per shared buffer = tr + 2 * GUARD */
 };
 
@@ -142,7 +153,7 @@ __device__ __forceinline__ TileGeom tile_geom(const TileArgs &ta)
     g.c1 = g.c0 + ta.tc4 < a.ncol4 ? g.c0 + ta.tc4 : a.ncol4;
     g.r0 = a.row0 + ty * ta.tr;
     g.r1 = g.r0 + ta.tr < a.row1 ? g.r0 + ta.tr : a.row1;
-    g.sp = 4 * (ta.tc4 + 2);
+    g.sp = ta.sp;
     g.srows = ta.tr + 2 * GUARD;
     return g;
 }
@@ -152,26 +163,55 @@ __device__ __forceinline__ float *tile_origin(float *buf, const TileGeom &g)
 {
     return buf + (long long)(GUARD - g.r0) * g.sp + (4 - 4 * g.c0);
 }
-/* whole tile incl. halo ring <- global level (rows r0-GUARD .. r1+GUARD, float4 columns c0-1 .. c1) */
-__device__ __forceinline__ void tile_load_all(float *buf, const float *glob, long long gpitch, const TileGeom &g)
+/* ---- sponge, applied where a value enters a tile buffer */
+struct TileSponge {
+    const float *tz, *tx; /* shared-memory copies of the tables, origins: tz[j], tx[global row] */
+};
+
+/* some factor can differ from 1 at (row gi, column j) (StepArgs::tap_*) */
+__device__ __forceinline__ bool tile_in_sponge(const StepArgs &a, int gi, int j)
+{
+    return j < a.tap_jlo || j >= a.tap_jhi || gi < a.tap_ilo || gi >= a.tap_ihi;
+}
+
+/* cnt applications of (v*Z)*X at (gi, j): kernel_tapper fd-code.cu:94-117, taper_apply taper.c:47-67; Z only on
+ * rows the reference's launch covered (tz_ilim), X only on the columns it applies to (tx_jlim) */
+__device__ __forceinline__ float tile_tap(const StepArgs &a, const TileSponge &sg, float v, int gi, int j, int cnt)
+{
+    if (cnt == 0 || !tile_in_sponge(a, gi, j)) return v;
+    const float zf = gi < a.tz_ilim ? sg.tz[j] : 1.0f;
+    const float xf = j < a.tx_jlim ? sg.tx[gi] : 1.0f;
+    for (int c = 0; c < cnt; c++) v = fmul(fmul(v, zf), xf);
+    return v;
+}
+
+__device__ __forceinline__ float4 tile_tap4(const StepArgs &a, const TileSponge &sg, float4 v, int gi, int j0, int cnt)
+{
+    if (cnt == 0) return v;
+    v.x = tile_tap(a, sg, v.x, gi, j0, cnt);
+    v.y = tile_tap(a, sg, v.y, gi, j0 + 1, cnt);
+    v.z = tile_tap(a, sg, v.z, gi, j0 + 2, cnt);
+    v.w = tile_tap(a, sg, v.w, gi, j0 + 3, cnt);
+    return v;
+}
+
+/* whole tile incl. halo ring <- global level (rows r0-GUARD .. r1+GUARD, float4 columns c0-1 .. c1), the sponge
+ * applied cnt times on the way in */
+__device__ __forceinline__ void tile_load_all(float *buf, const float *glob, long long gpitch, const TileGeom &g,
+                                              const StepArgs &a, const TileSponge &sg, int cnt)
 {
     const int w4 = g.c1 - g.c0 + 2, nr = g.r1 - g.r0 + 2 * GUARD;
     float *org = tile_origin(buf, g);
     for (int e = threadIdx.x; e < w4 * nr; e += blockDim.x) {
         const int r = g.r0 - GUARD + e / w4, q = g.c0 - 1 + e % w4;
         const float4 v = __ldcg(reinterpret_cast<const float4 *>(glob + (long long)r * gpitch + 4 * q));
-        st4(org + (long long)r * g.sp + 4 * q, v);
+        st4(org + (long long)r * g.sp + 4 * q, tile_tap4(a, sg, v, r, 4 * q, cnt));
     }
 }
 
-__device__ __forceinline__ void tile_zero(float *buf, const TileGeom &g)
-{
-    const int n4 = g.srows * g.sp / 4;
-    for (int e = threadIdx.x; e < n4; e += blockDim.x) st4(buf + 4 * e, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-}
-
 /* halo ring only: GUARD rows above and below (owned columns), one float4 column left and right (owned rows) */
-__device__ __forceinline__ void tile_load_ring(float *buf, const float *glob, long long gpitch, const TileGeom &g)
+__device__ __forceinline__ void tile_load_ring(float *buf, const float *glob, long long gpitch, const TileGeom &g,
+                                               const StepArgs &a, const TileSponge &sg, int cnt)
 {
     const int w4 = g.c1 - g.c0, nr = g.r1 - g.r0;
     const int nrow_part = 2 * GUARD * w4, ncol_part = 2 * nr;
@@ -188,8 +228,58 @@ __device__ __forceinline__ void tile_load_ring(float *buf, const float *glob, lo
             q = (k & 1) ? g.c1 : g.c0 - 1;
         }
         const float4 v = __ldcg(reinterpret_cast<const float4 *>(glob + (long long)r * gpitch + 4 * q));
-        st4(org + (long long)r * g.sp + 4 * q, v);
+        st4(org + (long long)r * g.sp + 4 * q, tile_tap4(a, sg, v, r, 4 * q, cnt));
     }
+}
+
+/* ---- flag-in-data halo exchange */
+__device__ __forceinline__ void ll_store(unsigned long long *slot, float v, unsigned tag)
+{
+    asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(slot), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ll_load(const unsigned long long *slot, unsigned &v, unsigned &tag)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(slot) : "memory");
+}
+
+/* halo ring <- the neighbours' {value, tag} pairs of level `tag`: GUARD rows above / below the owned columns,
+ * GUARD columns left / right of the owned rows; points outside the updated region never change and keep what
+ * the initial load put there.  false = a neighbour never delivered (wall-clock time-out). */
+__device__ __forceinline__ bool tile_poll_ring(float *buf, const unsigned long long *plane, long long gpitch, const TileGeom &g,
+                                               const StepArgs &a, const TileSponge &sg, int cnt, unsigned tag, int *error_flag,
+                                               unsigned long long timeout_ns)
+{
+    const int w = 4 * (g.c1 - g.c0), h = g.r1 - g.r0;
+    const int nrow_part = 2 * GUARD * w, ncol_part = 2 * GUARD * h;
+    float *org = tile_origin(buf, g);
+    const int jlo = 4 * a.col4_0, jhi = 4 * a.ncol4;
+    bool ok = true;
+    for (int e = threadIdx.x; e < nrow_part + ncol_part; e += blockDim.x) {
+        int r, j;
+        if (e < nrow_part) {
+            const int k = e / w;
+            r = k < GUARD ? g.r0 - GUARD + k : g.r1 + (k - GUARD);
+            j = 4 * g.c0 + e % w;
+        } else {
+            const int k = e - nrow_part, c = k % (2 * GUARD);
+            r = g.r0 + k / (2 * GUARD);
+            j = c < GUARD ? 4 * g.c0 - GUARD + c : 4 * g.c1 + (c - GUARD);
+        }
+        if (r < a.row0 || r >= a.row1 || j < jlo || j >= jhi) continue; /* nobody updates this point */
+        const unsigned long long *slot = plane + (long long)r * gpitch + j;
+        unsigned v, t;
+        ll_load(slot, v, t);
+        if (t != tag) {
+            const unsigned long long t0 = wall_ns();
+            unsigned spins = 0;
+            do {
+                ll_load(slot, v, t);
+                if ((++spins & 1023u) == 0 && wall_ns() - t0 > timeout_ns) { atomicExch(error_flag, 1); ok = false; break; }
+            } while (t != tag);
+        }
+        org[(long long)r * g.sp + j] = tile_tap(a, sg, __uint_as_float(v), r, j, cnt);
+    }
+    return ok;
 }
 
 /* the sponge tables of this tile's columns / rows, staged once (the acquire of every level's barrier
@@ -208,8 +298,11 @@ struct TilePt {
     unsigned o;   /* older level in, new level out */
     unsigned v;   /* fl32(v2*dt2) */
     unsigned f;   /* EPI_IMG_FIELD: reconstructed source level */
-    unsigned tz, tx; /* sponge tables: tz + 4*j, tx + 4*row */
     int sp;
+    int tap_o;    /* sponge applications still missing on the older level's stored values at this level */
+    int tap_new;  /* applications the new level needs as the NEXT level's stencil input (applied as it is stored) */
+    unsigned long long *ll; /* {value, tag} plane of the level being written (origin: global row 0, column 0); null = off */
+    unsigned tag;
 };
 
 __device__ __forceinline__ float lds(unsigned addr)
@@ -227,20 +320,9 @@ __device__ __forceinline__ unsigned tile_origin_s(const float *buf, const TileGe
     return (unsigned)__cvta_generic_to_shared(buf) + 4u * (unsigned)((GUARD - g.r0) * g.sp + (4 - 4 * g.c0));
 }
 
-/* sponge applied cnt times to one value at (row gi, column j): (v*Z)*X per application (kernel_tapper
- * fd-code.cu:94-117, taper_apply taper.c:47-67), Z only on rows the reference's launch covered (tz_ilim),
- * X only on the columns it applies to (tx_jlim) */
-/* (a real call on purpose: the rare path must not bloat the instruction footprint of the level loop) */
-static __device__ __noinline__ float tile_tap(const StepArgs &a, const TilePt &t, float v, int gi, int j, int cnt)
-{
-    const float zf = gi < a.tz_ilim ? lds(t.tz + 4u * (unsigned)j) : 1.0f;
-    const float xf = j < a.tx_jlim ? lds(t.tx + 4u * (unsigned)gi) : 1.0f;
-    for (int c = 0; c < cnt; c++) v = fmul(fmul(v, zf), xf);
-    return v;
-}
-
 template <int ORDER, int RECIPE, bool TAPER, int EPI>
-__device__ __forceinline__ void tile_point(const StepArgs &a, const Level &lv, const TilePt &t, const int gi, const int j)
+__device__ __forceinline__ void tile_point(const StepArgs &a, const Level &lv, const TilePt &t, const TileSponge &sg,
+                                           const int gi, const int j)
 {
     constexpr int H = ORDER / 2;
     const unsigned off = 4u * (unsigned)(gi * t.sp + j), rowb = 4u * (unsigned)t.sp;
@@ -253,16 +335,9 @@ __device__ __forceinline__ void tile_point(const StepArgs &a, const Level &lv, c
         if (k != H) x[k] = lds(ctr + (unsigned)(k - H) * rowb);
     float o = lds(t.o + off);
     const float v = lds(t.v + off);
-    /* sponge on load; all factors are exactly 1 away from the sponge (StepArgs::tap_*), where nothing is done */
-    if (TAPER && (lv.np | lv.no) &&
-        (j - H < a.tap_jlo || j + H >= a.tap_jhi || gi - H < a.tap_ilo || gi + H >= a.tap_ihi)) {
-#pragma unroll
-        for (int k = 0; k <= 2 * H; k++) z[k] = tile_tap(a, t, z[k], gi, j + k - H, lv.np);
-#pragma unroll
-        for (int k = 0; k <= 2 * H; k++)
-            if (k != H) x[k] = tile_tap(a, t, x[k], gi + k - H, j, lv.np);
-        o = tile_tap(a, t, o, gi, j, lv.no);
-    }
+    /* the newer level sits in the tile with its sponge applications done (they were applied as the values
+     * entered the buffer); the older level's own point may miss some */
+    if (TAPER) o = tile_tap(a, sg, o, gi, j, t.tap_o);
     x[H] = z[H];
     const float cc = z[H];
     float lap;
@@ -305,11 +380,12 @@ __device__ __forceinline__ void tile_point(const StepArgs &a, const Level &lv, c
         const long long idx = a.dobs_base + (long long)(gi - a.inj_gi0) * a.inj_nt + lv.inj_tidx;
         res = fadd(res, (idx >= 0 && idx < a.dobs_len) ? a.dobs[idx] : 0.0f);
     }
-    sts(t.o + off, res);
+    sts(t.o + off, TAPER ? tile_tap(a, sg, res, gi, j, t.tap_new) : res);
     lv.mirror[(long long)gi * a.apitch + j] = res;
+    if (t.ll) ll_store(t.ll + (long long)gi * a.apitch + j, res, t.tag);
     /* ---- side outputs (global memory, pitch a.apitch) */
     if ((EPI & EPI_RECORD) && j == a.rec_j && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n)
-        a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = TAPER ? tile_tap(a, t, cc, gi, j, 1) : cc;
+        a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = TAPER ? tile_tap(a, sg, cc, gi, j, 1) : cc;
     if ((EPI & EPI_HSTORE) && gi >= a.hist_gi0 && gi < a.hist_gi0 + a.hist_n)
         lv.hist_w[(long long)(gi - a.hist_gi0) * a.apitch + j] = cc;
     if ((EPI & EPI_IMG_HIST) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n) {
@@ -344,13 +420,14 @@ __device__ __forceinline__ TileWork tile_work(const TileGeom &g)
 }
 
 template <int ORDER, int RECIPE, bool TAPER, int EPI>
-__device__ __forceinline__ void tile_update(const StepArgs &a, const Level &lv, const TilePt &t, const TileWork &k)
+__device__ __forceinline__ void tile_update(const StepArgs &a, const Level &lv, const TilePt &t, const TileSponge &sg,
+                                            const TileWork &k)
 {
 #pragma unroll
     for (int r = 0; r < TileWork::KEEP; r++)
-        if ((int)(threadIdx.x + r * blockDim.x) < k.npts) tile_point<ORDER, RECIPE, TAPER, EPI>(a, lv, t, k.gi[r], k.j[r]);
+        if ((int)(threadIdx.x + r * blockDim.x) < k.npts) tile_point<ORDER, RECIPE, TAPER, EPI>(a, lv, t, sg, k.gi[r], k.j[r]);
     for (int p = threadIdx.x + TileWork::KEEP * blockDim.x; p < k.npts; p += blockDim.x)
-        tile_point<ORDER, RECIPE, TAPER, EPI>(a, lv, t, k.r0 + p / k.w, k.j00 + p % k.w);
+        tile_point<ORDER, RECIPE, TAPER, EPI>(a, lv, t, sg, k.r0 + p / k.w, k.j00 + p % k.w);
 }
 
 /* forward phases: nlevels levels of pair 0 (plain, modelling, rtm forward with history, rtm backward) */
@@ -362,32 +439,47 @@ __device__ __forceinline__ void tile_forward(const TileArgs &ta, float *smem)
     const TileGeom g = tile_geom(ta);
     __shared__ int lost;
     if (threadIdx.x == 0) lost = 0;
-    float *sbuf[2] = {smem, smem + (long long)g.srows * g.sp};
+    float *const sbuf0 = smem, *const sbuf1 = smem + (long long)g.srows * g.sp; /* (no arrays indexed by the level parity:
+                                                                                    they would live in local memory) */
     float *sv = smem + 2LL * g.srows * g.sp;
     float *stz = smem + 3LL * g.srows * g.sp, *stx = stz + g.sp + 8;
     tile_load_tables(stz, stx, a, g);
-    tile_load_all(sbuf[0], pa.bufN, a.apitch, g);
-    tile_load_all(sbuf[1], pa.bufO, a.apitch, g);
-    tile_load_all(sv, a.vdt, a.apitch, g);
+    __syncthreads();
+    TileSponge sg;
+    sg.tz = stz - (4 * g.c0 - 4);
+    sg.tx = stx - (g.r0 - GUARD);
+    /* the newer level enters its buffer with the sponge applications of level 0 done, the older one raw */
+    tile_load_all(sbuf0, pa.bufN, a.apitch, g, a, sg, persist_np(pa, 0));
+    tile_load_all(sbuf1, pa.bufO, a.apitch, g, a, sg, 0);
+    tile_load_all(sv, a.vdt, a.apitch, g, a, sg, 0);
     __syncthreads();
     const unsigned nblk = gridDim.x;
     const TileWork work = tile_work(g);
-    const unsigned org[2] = {tile_origin_s(sbuf[0], g), tile_origin_s(sbuf[1], g)};
+    const unsigned org0 = tile_origin_s(sbuf0, g), org1 = tile_origin_s(sbuf1, g);
     TilePt t;
     t.v = tile_origin_s(sv, g); t.f = 0; t.sp = g.sp;
-    t.tz = (unsigned)__cvta_generic_to_shared(stz) - 4u * (unsigned)(4 * g.c0 - 4);
-    t.tx = (unsigned)__cvta_generic_to_shared(stx) - 4u * (unsigned)(g.r0 - GUARD);
     for (int l = 0; l < pa.nlevels; l++) {
         Level lv = persist_level_of(pa, l);
-        float *gnew = lv.pp; /* global copy of the level being written */
+        float *gnew = lv.pp; /* global copy of the level being written (raw values, like every other kernel's) */
         lv.mirror = gnew;
-        t.n = org[l & 1];
-        t.o = org[(l & 1) ^ 1];
-        if (!(ta.dbg & 2)) tile_update<ORDER, RECIPE, true, EPI>(a, lv, t, work);
+        t.n = (l & 1) ? org1 : org0;
+        t.o = (l & 1) ? org0 : org1;
+        t.tap_o = lv.no - (l ? persist_np(pa, l - 1) : 0); /* the older level was the newer one of level l-1 */
+        t.tap_new = persist_np(pa, l + 1);
+        t.ll = ta.ll ? ta.ll + (l & 1) * ta.ll_plane : nullptr;
+        t.tag = (unsigned)(l + 1);
+        if (!(ta.dbg & 2)) tile_update<ORDER, RECIPE, true, EPI>(a, lv, t, sg, work);
         if (l + 1 == pa.nlevels) break; /* the kernel boundary orders the last level */
-        if (!(ta.dbg & 1) && !tile_sync(ta, (unsigned)(l + 1), nblk, &lost)) return;
-        if (!(ta.dbg & 4)) tile_load_ring(sbuf[(l & 1) ^ 1], gnew, a.apitch, g);
-        __syncthreads();
+        if (ta.ll) {
+            if (!tile_poll_ring((l & 1) ? sbuf0 : sbuf1, t.ll, a.apitch, g, a, sg, t.tap_new, t.tag, pa.error_flag, pa.timeout_ns))
+                lost = 1;
+            __syncthreads();
+            if (lost) return;
+        } else {
+            if (!(ta.dbg & 1) && !tile_sync(ta, (unsigned)(l + 1), nblk, &lost)) return;
+            if (!(ta.dbg & 4)) tile_load_ring((l & 1) ? sbuf0 : sbuf1, gnew, a.apitch, g, a, sg, t.tap_new);
+            __syncthreads();
+        }
     }
 }
 
@@ -404,38 +496,43 @@ __device__ __forceinline__ void tile_backward(const TileArgs &ta, float *smem)
     __shared__ int lost;
     if (threadIdx.x == 0) lost = 0;
     const long long bsz = (long long)g.srows * g.sp;
-    float *ss[2] = {smem, smem + bsz};           /* source field: [0] = u(T), [1] = u(T-1) at entry */
-    float *sr[2] = {smem + 2 * bsz, smem + 3 * bsz}; /* receiver field */
+    float *const ss0 = smem, *const ss1 = smem + bsz;               /* source field: u(T), u(T-1) at entry */
+    float *const sr0 = smem + 2 * bsz, *const sr1 = smem + 3 * bsz; /* receiver field */
     float *sv = smem + 4 * bsz;
     float *stz = smem + 5 * bsz, *stx = stz + g.sp + 8;
     tile_load_tables(stz, stx, a, g);
-    float *gs[2] = {ta.sav0, ta.sav1};
-    tile_load_all(ss[0], gs[0], a.apitch, g);
-    tile_load_all(ss[1], gs[1], a.apitch, g);
-    tile_load_all(sr[0], pa.bufN, a.apitch, g);
-    tile_load_all(sr[1], pa.bufO, a.apitch, g);
-    tile_load_all(sv, a.vdt, a.apitch, g);
+    __syncthreads();
+    TileSponge sg;
+    sg.tz = stz - (4 * g.c0 - 4);
+    sg.tx = stx - (g.r0 - GUARD);
+    float *const gs0 = ta.sav0, *const gs1 = ta.sav1;
+    tile_load_all(ss0, gs0, a.apitch, g, a, sg, 0);
+    tile_load_all(ss1, gs1, a.apitch, g, a, sg, 0);
+    tile_load_all(sr0, pa.bufN, a.apitch, g, a, sg, persist_np(pa, 0));
+    tile_load_all(sr1, pa.bufO, a.apitch, g, a, sg, 0);
+    tile_load_all(sv, a.vdt, a.apitch, g, a, sg, 0);
     __syncthreads();
     const unsigned nblk = gridDim.x;
     const TileWork work = tile_work(g);
-    const unsigned os[2] = {tile_origin_s(ss[0], g), tile_origin_s(ss[1], g)};
-    const unsigned orr[2] = {tile_origin_s(sr[0], g), tile_origin_s(sr[1], g)};
+    const unsigned os0 = tile_origin_s(ss0, g), os1 = tile_origin_s(ss1, g);
+    const unsigned or0 = tile_origin_s(sr0, g), or1 = tile_origin_s(sr1, g);
     TilePt t;
     t.v = tile_origin_s(sv, g); t.f = 0; t.sp = g.sp;
-    t.tz = (unsigned)__cvta_generic_to_shared(stz) - 4u * (unsigned)(4 * g.c0 - 4);
-    t.tx = (unsigned)__cvta_generic_to_shared(stx) - 4u * (unsigned)(g.r0 - GUARD);
     for (int it = 0; it < pa.nlevels; it++) {
         /* ---- source field: cur = index of the level the imaging condition uses at this step */
         int cur = it & 1; /* it = 0: u(T) in ss[0]; it = 1: u(T-1) in ss[1]; then the update writes ss[it & 1] */
         if (it >= 2) {
             Level ls;
             ls.p = nullptr; ls.pp = nullptr; ls.vdt = nullptr; ls.tz = nullptr; ls.tx = nullptr;
-            ls.mirror = gs[it & 1];
+            ls.mirror = (it & 1) ? gs1 : gs0;
             ls.np = ls.no = 0; ls.src_on = 0; ls.src_amp = 0.0f; ls.rec_it = 0; ls.inj_tidx = 0;
             ls.hist_w = nullptr; ls.hist_r = nullptr; ls.img_field = nullptr;
-            t.n = os[(it & 1) ^ 1]; /* prev1 */
-            t.o = os[it & 1];       /* prev2, overwritten */
-            tile_update<ORDER, RECIPE, false, 0>(a, ls, t, work);
+            t.n = (it & 1) ? os0 : os1; /* prev1 */
+            t.o = (it & 1) ? os1 : os0; /* prev2, overwritten */
+            t.tap_o = t.tap_new = 0;
+            t.ll = ta.ll ? ta.ll + (2 + (it & 1)) * ta.ll_plane : nullptr; /* planes 2, 3: the source field */
+            t.tag = (unsigned)(it + 1);
+            tile_update<ORDER, RECIPE, false, 0>(a, ls, t, sg, work);
             /* no barrier: the imaging below reads this level only at the thread's own points (same point-to-thread
              * mapping in both updates) */
         }
@@ -444,15 +541,30 @@ __device__ __forceinline__ void tile_backward(const TileArgs &ta, float *smem)
         float *gnew = lv.pp;
         lv.mirror = gnew;
         lv.src_on = 0;
-        t.n = orr[it & 1];
-        t.o = orr[(it & 1) ^ 1];
-        t.f = os[cur];
-        tile_update<ORDER, RECIPE, true, EPI_INJECT | EPI_IMG_FIELD>(a, lv, t, work);
+        t.n = (it & 1) ? or1 : or0;
+        t.o = (it & 1) ? or0 : or1;
+        t.f = cur ? os1 : os0;
+        t.tap_o = lv.no - (it ? persist_np(pa, it - 1) : 0);
+        t.tap_new = persist_np(pa, it + 1);
+        t.ll = ta.ll ? ta.ll + (it & 1) * ta.ll_plane : nullptr; /* planes 0, 1: the receiver field */
+        t.tag = (unsigned)(it + 1);
+        tile_update<ORDER, RECIPE, true, EPI_INJECT | EPI_IMG_FIELD>(a, lv, t, sg, work);
         if (it + 1 == pa.nlevels) break;
-        if (!tile_sync(ta, (unsigned)(it + 1), nblk, &lost)) return;
-        if (it >= 2) tile_load_ring(ss[it & 1], gs[it & 1], a.apitch, g);
-        tile_load_ring(sr[(it & 1) ^ 1], gnew, a.apitch, g);
-        __syncthreads();
+        if (ta.ll) {
+            bool ok = true;
+            if (it >= 2)
+                ok = tile_poll_ring((it & 1) ? ss1 : ss0, ta.ll + (2 + (it & 1)) * ta.ll_plane, a.apitch, g, a, sg, 0, t.tag,
+                                    pa.error_flag, pa.timeout_ns);
+            ok = tile_poll_ring((it & 1) ? sr0 : sr1, t.ll, a.apitch, g, a, sg, t.tap_new, t.tag, pa.error_flag, pa.timeout_ns) && ok;
+            if (!ok) lost = 1;
+            __syncthreads();
+            if (lost) return;
+        } else {
+            if (!tile_sync(ta, (unsigned)(it + 1), nblk, &lost)) return;
+            if (it >= 2) tile_load_ring((it & 1) ? ss1 : ss0, (it & 1) ? gs1 : gs0, a.apitch, g, a, sg, 0);
+            tile_load_ring((it & 1) ? sr0 : sr1, gnew, a.apitch, g, a, sg, t.tap_new);
+            __syncthreads();
+        }
     }
 }
 

@@ -20,16 +20,21 @@ with fdw.Wave2D(nx, nz, nb, nb, 10.0, 10.0, 0.001, order=8, fac=0.75, family=fdw
     t0 = time.perf_counter(); w.forward(nb + 10, nb, download=False); w.backward(dobs, nb); b = (time.perf_counter() - t0) * 1e3 - f
     print("RESULT %%.3f %%.3f %%d" %% (f / nt * 1e3, b / nt * 1e3, w.tile_launches()))
 ''' % ROOT
-cases = {"new_mod": (315, 195, 50, 1700), "marmousi": (369, 375, 40, 3004)}
+cases = {"new_mod": (315, 195, 50, 1700), "3lay_mod": (151, 151, 40, 1001), "marmousi": (369, 375, 40, 3004)}
+settings = [("flag-in-data halo (default)", {}),
+            ("neighbour flags + ring loads (FDW_TILE_LL=0)", {"FDW_TILE_LL": "0"}),
+            ("counter barrier + ring loads (FDW_TILE_LL=0, dbg 8)", {"FDW_TILE_LL": "0", "FDW_TILE_DBG": "8"}),
+            ("flags, no barrier (dbg 1)", {"FDW_TILE_LL": "0", "FDW_TILE_DBG": "1"}),
+            ("flags, no update (dbg 2)", {"FDW_TILE_LL": "0", "FDW_TILE_DBG": "2"}),
+            ("flags, no ring load (dbg 4)", {"FDW_TILE_LL": "0", "FDW_TILE_DBG": "4"}),
+            ("L2-resident persistent kernel of round 1 (FDW_TILE=0)", {"FDW_TILE": "0"})]
 for name, dims in cases.items():
-    for dbg in (0, 8, 1, 2, 4, 3, 5, 6, 7):
-        env = dict(os.environ, FDW_TILE_DBG=str(dbg), FDW_TILE_VERBOSE="1" if dbg == 0 else "")
-        if dbg == 0:
-            env.pop("FDW_TILE_DBG")
-        if not env["FDW_TILE_VERBOSE"]:
-            env.pop("FDW_TILE_VERBOSE")
+    for label, extra in settings:
+        env = dict(os.environ, **extra)
+        if not extra:
+            env["FDW_TILE_VERBOSE"] = "1"
         r = subprocess.run([sys.executable, "-c", CHILD] + [str(x) for x in dims], capture_output=True, text=True, env=env)
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
         plan = [l for l in r.stderr.splitlines() if "tile plan" in l][:1]
-        print(name, "dbg", dbg, "(no:%s%s%s)" % (" barrier" if dbg & 1 else "", " update" if dbg & 2 else "", " ring" if dbg & 4 else ""),
-              ("(counter barrier) " if dbg & 8 else "") + "fwd us/level, bwd us/level, tile launches:", line[0][7:] if line else r.stderr[-300:], plan[0] if plan else "", flush=True)
+        print("%-9s %-52s fwd us/level, bwd us/level, tile launches: %s %s" % (name, label, line[0][7:] if line else r.stderr[-300:],
+                                                                            plan[0] if plan else ""), flush=True)
