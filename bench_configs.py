@@ -298,7 +298,8 @@ def c5_domain_divided(device, rank, world):
     sp.model_shot(sx, sz, gz)
     rows, dt = timed(lambda: sp.model_shot(sx, sz, gz))
     g = pts * nt / dt / 1e9
-    out["mod_main"] = dict(value=g, unit="Gpts/s", us_per_level=dt / nt * 1e6, per_gpu=_roof(g / world, 16))
+    out["mod_main"] = dict(value=g, unit="Gpts/s", us_per_level=dt / nt * 1e6, per_gpu=_roof(g / world, 16),
+                           level_loop_us_per_level_device_rank0=sp.levels_ms.get(fdw.PHASE_MODEL, 0.0) / nt * 1e3)
     data = sp.gather_rows(rows)
     sp.close()
     sp = D.SlabPropagator(nx, nz, nb, nb, 10.0, 10.0, 0.001, taper=fdw.TAPER_TOP, history=True, **kw)
@@ -307,7 +308,10 @@ def c5_domain_divided(device, rank, world):
     sp.rtm_shot_cpu(sx, sz, gz, data[None], 0)
     _, dt = timed(lambda: sp.rtm_shot_cpu(sx, sz, gz, data[None], 0))
     g = 2 * pts * nt / dt / 1e9
-    out["rtm_main"] = dict(value=g, unit="Gpts/s", us_per_level=dt / (2 * nt) * 1e6, per_gpu=_roof(g / world, 22))
+    out["rtm_main"] = dict(value=g, unit="Gpts/s", us_per_level=dt / (2 * nt) * 1e6, per_gpu=_roof(g / world, 22),
+                           forward_level_loop_us_per_level_device_rank0=sp.levels_ms.get(fdw.PHASE_RTM_FWD, 0.0) / nt * 1e3,
+                           backward_level_loop_us_per_level_device_rank0=sp.levels_ms.get(fdw.PHASE_RTM_BWD, 0.0) / nt * 1e3)
+    out["persistent_slab_launches_rank0"] = int(sp.w.pslab_launches())
     out["history_GB_per_gpu"] = nt * max(sp.owned_interior()[1], 0) * ((nze + 4 + 31) // 32 * 32) * 4 / 1e9
     out["halo"] = "p2p" if sp.p2p else "nccl"
     sp.close()

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfdwave.so")
+LIB_PATH = os.environ.get("FDW_LIBFDWAVE") or os.path.join(_HERE, "libfdwave.so")  # (override: A/B of two builds in tools/)
 
 FAMILY_GPU, FAMILY_CPU = 0, 1
 RECIPE_G, RECIPE_C, RECIPE_FAST = 0, 1, 2

@@ -73,6 +73,7 @@ class SlabPropagator:
                         lib=lib, **kw)
         self.L, self.h = self.w.L, self.w.h
         self._views = {}
+        self.levels_ms = {}
         self._compute_stream = None
         self._comm_stream = None
         self._event = None
@@ -238,7 +239,11 @@ class SlabPropagator:
         _lib.check(L, L.fdw_shot_begin(h, phase, sx, sz, gz, ptr, ns, is_))
         if self.p2p:
             self._peer_refresh()  # the phase zeroed the fields
+        if self.on_gpu:
+            self.w.mark_begin()
         self._levels(0, self.w.nt)
+        if self.on_gpu:  # device time of the level loop of this phase (CUDA events on the library's stream)
+            self.levels_ms[phase] = self.w.mark_end()
 
     def model_shot(self, sx, sz, gz):
         """one shot of mod_main (mod_main.cpp:141-169) on the slab-decomposed grid; returns this
