@@ -62,7 +62,8 @@ typedef struct fdw_ctx fdw_ctx;
 typedef struct fdw_params {
     int nx, nz;   /* interior grid */
     int nxb, nzb; /* sponge / border widths */
-    int order;    /* 2, 4, 6 or 8 */
+    int order;    /* even, 2..16; 2-8 are the tabulated weights, 10-16 the makeo2 windowed-sinc ones (functions.c:119-157).
+                   * Orders above 8 run whole-grid contexts only (no slab decomposition: slabs exchange 4 ghost rows) */
     float dx, dz, dt;
     float fac;          /* sponge factor (meaning differs per family, see fdw_taper_table) */
     int family;         /* FDW_FAMILY_*: tables + step ordering */

@@ -30,6 +30,7 @@
 #include "fdw_step_core.h"
 
 using fdw::GUARD;
+using fdw::AGUARD;
 using fdw::StepArgs;
 using fdw::PersistArgs;
 using fdw::TileArgs;
@@ -98,7 +99,7 @@ struct fdw_ctx {
     cudaEvent_t ev_staged = nullptr, ev_shot_done = nullptr;
     bool staged = false, shot_done_valid = false;
     float *tz_base = nullptr, *tz = nullptr, *tx_base = nullptr, *tx = nullptr;
-    float cz[9], cx[9], dz2inv, dx2inv, dt2;
+    float cz[fdw::MAX_ORDER + 1], cx[fdw::MAX_ORDER + 1], dz2inv, dx2inv, dt2;
     int tx_jlim, tz_ilim, tap_jlo, tap_jhi, tap_ilo, tap_ihi;
     int lap_i0, lap_i1, lap_j0, lap_j1, upd_i1, upd_j1, ncol4;
     std::vector<float> wavelet;
@@ -155,6 +156,7 @@ struct fdw_ctx {
     std::vector<RecLaunch> lshape;         /* the launch list the graph was built from */
     int use_graph = 1;
     long long graph_replays = 0;
+    int use_multirect = 1;       /* the sponge strips of a level in ONE launch (FDW_MULTIRECT=0: one launch per strip) */
     /* split-phase step (slab decomposition) */
     bool step_open = false;
     StepArgs step_args;
@@ -253,6 +255,10 @@ static const void *step_kernel(int order, int recipe, int epi, int sponge)
     case 4: return fdw_step_kernel_o4(recipe, epi, sponge);
     case 6: return fdw_step_kernel_o6(recipe, epi, sponge);
     case 8: return fdw_step_kernel_o8(recipe, epi, sponge);
+    case 10: return fdw_step_kernel_o10(recipe, epi, sponge);
+    case 12: return fdw_step_kernel_o12(recipe, epi, sponge);
+    case 14: return fdw_step_kernel_o14(recipe, epi, sponge);
+    case 16: return fdw_step_kernel_o16(recipe, epi, sponge);
     }
     return nullptr;
 }
@@ -264,6 +270,10 @@ static const void *persist_kernel(int order, int recipe, int epi)
     case 4: return fdw_persist_kernel_o4(recipe, epi);
     case 6: return fdw_persist_kernel_o6(recipe, epi);
     case 8: return fdw_persist_kernel_o8(recipe, epi);
+    case 10: return fdw_persist_kernel_o10(recipe, epi);
+    case 12: return fdw_persist_kernel_o12(recipe, epi);
+    case 14: return fdw_persist_kernel_o14(recipe, epi);
+    case 16: return fdw_persist_kernel_o16(recipe, epi);
     }
     return nullptr;
 }
@@ -275,6 +285,10 @@ static const void *tile_kernel(int order, int recipe, int epi)
     case 4: return fdw_tile_kernel_o4(recipe, epi);
     case 6: return fdw_tile_kernel_o6(recipe, epi);
     case 8: return fdw_tile_kernel_o8(recipe, epi);
+    case 10: return fdw_tile_kernel_o10(recipe, epi);
+    case 12: return fdw_tile_kernel_o12(recipe, epi);
+    case 14: return fdw_tile_kernel_o14(recipe, epi);
+    case 16: return fdw_tile_kernel_o16(recipe, epi);
     }
     return nullptr;
 }
@@ -286,6 +300,10 @@ static const void *pslab_kernel(int order, int recipe, int epi)
     case 4: return fdw_pslab_kernel_o4(recipe, epi);
     case 6: return fdw_pslab_kernel_o6(recipe, epi);
     case 8: return fdw_pslab_kernel_o8(recipe, epi);
+    case 10: return fdw_pslab_kernel_o10(recipe, epi);
+    case 12: return fdw_pslab_kernel_o12(recipe, epi);
+    case 14: return fdw_pslab_kernel_o14(recipe, epi);
+    case 16: return fdw_pslab_kernel_o16(recipe, epi);
     }
     return nullptr;
 }
@@ -297,11 +315,17 @@ static const void *lap_kernel(int order)
     case 4: return fdw_lap_kernel_o4();
     case 6: return fdw_lap_kernel_o6();
     case 8: return fdw_lap_kernel_o8();
+    case 10: return fdw_lap_kernel_o10();
+    case 12: return fdw_lap_kernel_o12();
+    case 14: return fdw_lap_kernel_o14();
+    case 16: return fdw_lap_kernel_o16();
     }
     return nullptr;
 }
 
-static long long pitch_for(int nze) { return ((long long)nze + 4 + 31) / 32 * 32; }
+/* row pitch: >= order/2 zero pad columns after the valid ones (they absorb the z-neighbour loads of the edge threads
+ * on both sides: the left neighbours of column 0 are the previous row's pad), whole 128-byte lines */
+static long long pitch_for(int nze, int order) { return ((long long)nze + (order > 8 ? 8 : 4) + 31) / 32 * 32; }
 
 /* launch geometry: one thread per float4 column; CTAs tile z, x is cut into chunks of rows_per_cta
  * rows.  Measured on B200, interleaved in one process (tools/sweep_geometry.py, profiles/
@@ -324,6 +348,7 @@ static int cached_occupancy(const void *kern, int nthreads)
     return occ;
 }
 
+static double g_fill_waves = 2.0; /* FDW_FILL_WAVES */
 static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int thr_override, int rpc_override,
                             dim3 *grid, dim3 *block, int *rows_per_cta)
 {
@@ -337,7 +362,7 @@ static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int 
     } else {
         const long long cap = (long long)nsm * cached_occupancy(kern, nthreads);
         /* small problems: shorten the chunks until the grid fills the machine twice over */
-        while (rpc > 2 && (long long)gx * ((rows + rpc - 1) / rpc) < 2 * cap) rpc = (rpc + 1) / 2;
+        while (rpc > 2 && (double)gx * ((rows + rpc - 1) / rpc) < g_fill_waves * (double)cap) rpc = (rpc + 1) / 2;
     }
     while ((rows + rpc - 1) / rpc > 65535) rpc *= 2; /* gridDim.y limit */
     int gy = (rows + rpc - 1) / rpc;
@@ -413,6 +438,51 @@ static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, co
     return FDW_OK;
 }
 
+/* several disjoint rectangles of one level in ONE launch of the sponge kernel (StepArgs::nrect): the strips are
+ * latency-bound short kernels (a few thousand one-warp CTAs, ~10-20 us each on an 8272 x 2128 grid) -- one after the
+ * other on the side stream they outlast the bulk launch they are meant to hide behind (measured: 4 strips
+ * 20+20+10+10 us against a 53 us bulk, profiles/r02k_c5_launches.csv); side by side they take as long as the
+ * slowest.  Returns FDW_ERR_UNSUPPORTED (nothing launched) when the rectangles cannot share a launch. */
+static int launch_rects(fdw_ctx *c, const StepArgs &base, int recipe, int epi, const Rect *rc, int n, cudaStream_t st)
+{
+    const void *k = step_kernel(c->prm.order, recipe, epi, 1);
+    if (!k || n > (int)fdw::MAX_RECTS) return FDW_ERR_UNSUPPORTED;
+    StepArgs a = base;
+    a.nrect = 0;
+    long long total = 0;
+    unsigned threads = 0;
+    for (int i = 0; i < n; i++) {
+        if (rc[i].c1 <= rc[i].c0 || rc[i].r1 <= rc[i].r0) continue;
+        if (!rc[i].sponge) return FDW_ERR_UNSUPPORTED;
+        dim3 grid, block;
+        int rpc;
+        launch_geometry(k, c->nsm, rc[i].c1 - rc[i].c0, rc[i].r1 - rc[i].r0, c->threads_override, c->rows_per_cta_override,
+                        &grid, &block, &rpc);
+        if (threads && block.x != threads) return FDW_ERR_UNSUPPORTED;
+        threads = block.x;
+        StepArgs::RectGeom &g = a.rect[a.nrect++];
+        g.c0 = rc[i].c0; g.c1 = rc[i].c1; g.r0 = rc[i].r0; g.r1 = rc[i].r1; g.rpc = rpc; g.nbx = (int)grid.x;
+        g.cta0 = (int)total;
+        total += (long long)grid.x * grid.y;
+    }
+    if (a.nrect < 2 || total > 0x7fffffffLL) return FDW_ERR_UNSUPPORTED;
+    a.col4_0 = a.rect[0].c0; a.ncol4 = a.rect[0].c1; a.row0 = a.rect[0].r0; a.row1 = a.rect[0].r1; a.rows_per_cta = a.rect[0].rpc;
+    const dim3 grid((unsigned)total, 1, 1), block(threads, 1, 1);
+    c->launches++;
+    if (c->rec) {
+        RecLaunch r;
+        r.kern = k; r.grid = grid; r.block = block; r.kind = 0;
+        r.side = c->rec_lane >= 0 ? c->rec_lane : (st == c->side && st != c->stream);
+        r.par = c->rec_par;
+        r.level = c->rec_level; r.a = a;
+        c->rec->push_back(r);
+        return FDW_OK;
+    }
+    void *params[] = {&a};
+    CU(cudaLaunchKernel(k, grid, block, params, 0, st));
+    return FDW_OK;
+}
+
 /* number of CTAs launch_rect will use for this rectangle (same geometry code) */
 static long long rect_ctas(fdw_ctx *c, int recipe, int epi, const Rect &rc)
 {
@@ -458,10 +528,12 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
             Rect all = {0, nc, row0, row1, 1};
             return launch_rect(c, base, recipe, epi, all, st);
         }
-        /* columns whose own samples or z neighbours (+-4) sit in a z sponge, in whole warps */
+        /* columns whose own samples or z neighbours (whole float4 blocks: +-4, +-8 above order 8) sit in a z
+         * sponge, in whole warps */
+        const int zr = H > 4 ? 8 : 4;
         int cs = 0, cb = nc;
-        if (c->tap_jlo > INT_MIN) cs = (((c->tap_jlo + 4 + 3) / 4) + 31) / 32 * 32;
-        if (c->tap_jhi < INT_MAX) cb = ((c->tap_jhi - 7 > 0 ? c->tap_jhi - 7 : 0) / 4) / 32 * 32;
+        if (c->tap_jlo > INT_MIN) cs = (((c->tap_jlo + zr + 3) / 4) + 31) / 32 * 32;
+        if (c->tap_jhi < INT_MAX) cb = ((c->tap_jhi - 3 - zr > 0 ? c->tap_jhi - 3 - zr : 0) / 4) / 32 * 32;
         if (cs > nc) cs = nc;
         if (cb < cs) cb = cs;
         /* rows whose x window touches an x sponge that applies to every column */
@@ -486,6 +558,11 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
         CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
     }
     if (c->rec && do_fork) c->rec_lane = 2;
+    if (c->use_multirect && nside > 1) {
+        const int rc = launch_rects(c, base, recipe, epi, side, nside, ss);
+        if (rc == FDW_OK) nside = 0; /* all strips are in flight */
+        else if (rc != FDW_ERR_UNSUPPORTED) { c->rec_lane = -1; return rc; }
+    }
     for (int k = 0; k < nside; k++) {
         if (c->rec && do_fork) c->rec_par = 1; /* disjoint rectangles of one level */
         int rc = launch_rect(c, base, recipe, epi, side[k], ss);
@@ -599,7 +676,7 @@ static int tile_launch(fdw_ctx *c, const void *k, TileArgs &ta, const TilePlan &
         if (!c->ll_d && cudaMalloc(&c->ll_d, bytes) != cudaSuccess) { (void)cudaGetLastError(); c->ll_d = nullptr; }
         if (c->ll_d) {
             if (cudaMemsetAsync(c->ll_d, 0, bytes, c->stream) != cudaSuccess) return 0;
-            ta.ll = c->ll_d + (size_t)(GUARD + 1) * c->pitch; /* local row 0, column 0 of plane 0 */
+            ta.ll = c->ll_d + (size_t)(AGUARD + 1) * c->pitch; /* local row 0, column 0 of plane 0 */
             ta.ll_plane = (long long)plane;
         }
     }
@@ -793,7 +870,7 @@ static int field_alloc(fdw_ctx *c, Field *f)
 {
     CU(cudaMalloc(&f->base, c->field_elems * sizeof(float)));
     CU(cudaMemsetAsync(f->base, 0, c->field_elems * sizeof(float), c->stream));
-    f->r0 = f->base + (size_t)(GUARD + 1) * c->pitch;
+    f->r0 = f->base + (size_t)(AGUARD + 1) * c->pitch;
     f->pend = 0;
     return FDW_OK;
 }
@@ -803,7 +880,7 @@ static int field_zero(fdw_ctx *c, Field *f)
     /* With a neighbour attached, the ghost rows on that side belong to the neighbour's fdw_peer_refresh, which
      * may land before or after this memset: they are left alone (the refresh that must follow a zero on every
      * slab overwrites them), only the owned rows and the ghost rows of a physical grid edge are cleared. */
-    const size_t ghost = (size_t)(GUARD + 1) * c->pitch;
+    const size_t ghost = (size_t)(AGUARD + 1) * c->pitch;
     float *lo = f->base + (c->peer[0].on ? ghost : 0);
     float *hi = f->base + c->field_elems - (c->peer[1].on ? ghost : 0);
     CU(cudaMemsetAsync(lo, 0, (size_t)(hi - lo) * sizeof(float), c->stream));
@@ -845,8 +922,8 @@ static void build_sponge_tables(fdw_ctx *c, std::vector<float> &tz, std::vector<
     std::vector<float> tabx(p.nxb > 0 ? p.nxb : 1), tabz(p.nzb > 0 ? p.nzb : 1);
     fdw_taper_table(p.nxb, p.fac, p.family, tabx.data());
     fdw_taper_table(p.nzb, p.fac, p.family, tabz.data());
-    tz.assign((size_t)c->pitch + 8, 1.0f); /* index 4 + j */
-    tx.assign((size_t)c->nloc + 2 * GUARD, 1.0f); /* index GUARD + local row */
+    tz.assign((size_t)c->pitch + 2 * AGUARD, 1.0f); /* index AGUARD + j */
+    tx.assign((size_t)c->nloc + 2 * AGUARD, 1.0f); /* index AGUARD + local row */
     c->tx_jlim = INT_MAX; c->tz_ilim = INT_MAX;
     c->tap_jlo = INT_MIN; c->tap_jhi = INT_MAX; c->tap_ilo = INT_MIN; c->tap_ihi = INT_MAX;
     if (p.taper == FDW_TAPER_NONE) return;
@@ -855,14 +932,14 @@ static void build_sponge_tables(fdw_ctx *c, std::vector<float> &tz, std::vector<
         nzb_eff = (p.nzb / 8) * 8;            /* gridBorder_z, fd-code.cu:192-195 */
         c->tz_ilim = (c->nxe / 8) * 8;        /* z factor only on launched rows */
     }
-    for (int j = 0; j < nzb_eff; j++) tz[4 + j] = tabz[j];
+    for (int j = 0; j < nzb_eff; j++) tz[AGUARD + j] = tabz[j];
     if (p.taper == FDW_TAPER_FOUR)
-        for (int j = p.nz + p.nzb; j < c->nze; j++) tz[4 + j] = tabz[c->nze - 1 - j];
-    for (int lr = -GUARD; lr < c->nloc + GUARD; lr++) {
+        for (int j = p.nz + p.nzb; j < c->nze; j++) tz[AGUARD + j] = tabz[c->nze - 1 - j];
+    for (int lr = -AGUARD; lr < c->nloc + AGUARD; lr++) {
         int gi = c->gx0 + lr;
         if (gi < 0 || gi >= c->nxe) continue;
-        if (gi < p.nxb) tx[GUARD + lr] = tabx[gi];
-        else if (gi >= c->nxe - p.nxb) tx[GUARD + lr] = tabx[c->nxe - 1 - gi];
+        if (gi < p.nxb) tx[AGUARD + lr] = tabx[gi];
+        else if (gi >= c->nxe - p.nxb) tx[AGUARD + lr] = tabx[c->nxe - 1 - gi];
     }
     if (p.taper == FDW_TAPER_TOP) {
         c->tx_jlim = nzb_eff; /* x factor only on the two top corners */
@@ -881,8 +958,14 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
         fdw_set_error("fdw_create: bad grid %dx%d border %d,%d", prm->nx, prm->nz, prm->nxb, prm->nzb);
         return FDW_ERR_ARG;
     }
-    if (prm->order != 2 && prm->order != 4 && prm->order != 6 && prm->order != 8) {
-        fdw_set_error("fdw_create: order %d not supported on the device (2,4,6,8)", prm->order);
+    if (prm->order < 2 || prm->order > fdw::MAX_ORDER || (prm->order & 1)) {
+        fdw_set_error("fdw_create: order %d not supported on the device (even, 2..%d)", prm->order, (int)fdw::MAX_ORDER);
+        return FDW_ERR_UNSUPPORTED;
+    }
+    if (prm->order > 2 * GUARD && prm->slab_x1 > prm->slab_x0 &&
+        (prm->slab_x0 > 0 || prm->slab_x1 < prm->nx + 2 * prm->nxb)) {
+        fdw_set_error("fdw_create: slab decomposition exchanges %d ghost rows: order %d needs the whole grid on one GPU",
+                      (int)GUARD, prm->order);
         return FDW_ERR_UNSUPPORTED;
     }
     int ndev = fdw_device_count();
@@ -912,8 +995,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
         int hi = prm->nxb + prm->nx < c->gx0 + c->nloc ? prm->nxb + prm->nx : c->gx0 + c->nloc;
         c->nli = hi > c->li0 ? hi - c->li0 : 0;
     }
-    c->pitch = pitch_for(c->nze);
-    c->rows_alloc = (size_t)c->nloc + 2 * GUARD + 2;
+    c->pitch = pitch_for(c->nze, prm->order);
+    c->rows_alloc = (size_t)c->nloc + 2 * AGUARD + 2;
     c->field_elems = c->rows_alloc * (size_t)c->pitch;
     int rc = bind(c);
     if (rc != FDW_OK) { delete c; return rc; }
@@ -931,12 +1014,14 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_PSLAB_LIMIT")) c->pslab_limit = atoll(e);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
+    if (const char *e = getenv("FDW_FILL_WAVES")) g_fill_waves = atof(e);
+    if (const char *e = getenv("FDW_MULTIRECT")) c->use_multirect = atoi(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
     if (const char *e = getenv("FDW_FUSE_FLAGS")) c->fuse_flags = atoi(e);
     if (const char *e = getenv("FDW_TIMEOUT_MS")) c->timeout_ns = 1000000ull * (unsigned long long)atoll(e);
 
     /* coefficients and scalars: fd-code.cu:203-217 / fd.c:12-16 */
-    float coefs[9];
+    float coefs[fdw::MAX_ORDER + 1];
     fdw_calc_coefs(prm->order, prm->family, coefs);
     c->dx2inv = (1. / prm->dx) * (1. / prm->dx);
     c->dz2inv = (1. / prm->dz) * (1. / prm->dz);
@@ -992,15 +1077,15 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     c->newest[0] = 0; c->older[0] = 1; c->newest[1] = 2; c->older[1] = 3;
     TRY(cudaMalloc(&c->vdt_base, c->field_elems * sizeof(float)));
     TRY(cudaMemsetAsync(c->vdt_base, 0, c->field_elems * sizeof(float), c->stream));
-    c->vdt = c->vdt_base + (size_t)(GUARD + 1) * c->pitch;
+    c->vdt = c->vdt_base + (size_t)(AGUARD + 1) * c->pitch;
     std::vector<float> tz, tx;
     build_sponge_tables(c, tz, tx);
     TRY(cudaMalloc(&c->tz_base, tz.size() * sizeof(float)));
     TRY(cudaMalloc(&c->tx_base, tx.size() * sizeof(float)));
     TRY(cudaMemcpyAsync(c->tz_base, tz.data(), tz.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     TRY(cudaMemcpyAsync(c->tx_base, tx.data(), tx.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    c->tz = c->tz_base + 4;
-    c->tx = c->tx_base + GUARD;
+    c->tz = c->tz_base + AGUARD;
+    c->tx = c->tx_base + AGUARD;
     const size_t img_elems = (size_t)(c->nli > 0 ? c->nli : 1) * c->pitch; /* image/history rows = owned interior rows */
     TRY(cudaMalloc(&c->img, img_elems * sizeof(float)));
     TRY(cudaMemsetAsync(c->img, 0, img_elems * sizeof(float), c->stream));
@@ -1319,7 +1404,7 @@ extern "C" int fdw_v2_stage(fdw_ctx *c, const float *v2)
     }
     /* the staging buffer was the current velocity until the last commit: wait for the work enqueued before it */
     if (c->shot_done_valid) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_shot_done, 0));
-    float *r0 = c->vdt2_base + (size_t)(GUARD + 1) * c->pitch;
+    float *r0 = c->vdt2_base + (size_t)(AGUARD + 1) * c->pitch;
     int lo = -GUARD, hi = c->nloc + GUARD;
     if (c->gx0 + lo < 0) lo = -c->gx0;
     if (c->gx0 + hi > c->nxe) hi = c->nxe - c->gx0;
@@ -1348,7 +1433,7 @@ extern "C" int fdw_v2_commit(fdw_ctx *c)
     float *t = c->vdt_base;
     c->vdt_base = c->vdt2_base;
     c->vdt2_base = t;
-    c->vdt = c->vdt_base + (size_t)(GUARD + 1) * c->pitch;
+    c->vdt = c->vdt_base + (size_t)(AGUARD + 1) * c->pitch;
     c->staged = false;
     graph_drop_if_any(c);
     return FDW_OK;
@@ -1837,7 +1922,7 @@ static float *peer_image(const fdw_ctx *c, int side, int k)
 {
     const fdw_ctx::PeerSide &p = c->peer[side];
     if (!p.on) return nullptr;
-    float *r0 = p.fbase[k] + (size_t)(GUARD + 1) * c->pitch;
+    float *r0 = p.fbase[k] + (size_t)(AGUARD + 1) * c->pitch;
     return side == 0 ? r0 + (long long)p.nloc * c->pitch : r0 - (long long)c->nloc * c->pitch;
 }
 

@@ -46,7 +46,12 @@ namespace fdw {
 
 enum { RECIPE_G = 0, RECIPE_C = 1, RECIPE_FAST = 2 };
 enum { EPI_RECORD = 1, EPI_INJECT = 2, EPI_HSTORE = 4, EPI_IMG_HIST = 8, EPI_IMG_FIELD = 16, EPI_PUSH = 32 };
-enum { GUARD = 4 }; /* guard/ghost rows above and below every slab; >= order/2 */
+enum { GUARD = 4 };  /* ghost rows exchanged between slabs (orders <= 8; slab decomposition needs order/2 <= GUARD) */
+enum { AGUARD = 8 }; /* zero guard rows allocated above and below every slab; >= order/2 for every supported order */
+enum { MAX_ORDER = 16 };
+enum { MAX_RECTS = 5 };
+/* float4 blocks of z neighbours a thread loads on each side of its own float4 column */
+constexpr int zblocks(int order) { return (order / 2 + 3) / 4; }
 
 struct StepArgs {
     const float *p;  /* newer level, local row 0 / column 0; stencil input, never written */
@@ -61,14 +66,14 @@ struct StepArgs {
     int grow0;       /* global x index of local row 0 */
     int lap_i0, lap_i1, lap_j0, lap_j1; /* Laplacian is non-zero only inside (global) */
     int nze;         /* valid columns per row */
-    float cz[9], cx[9]; /* G/FAST: premultiplied weights; C: both hold the raw weights */
+    float cz[MAX_ORDER + 1], cx[MAX_ORDER + 1]; /* G/FAST: premultiplied weights; C: both hold the raw weights */
     float dz2inv, dx2inv;
     float one;        /* 1.0f, opaque to the assembler: the packed IEEE add is fma(acc, one, prod) */
     /* sponge */
     int taper_on;
     int np, no;       /* multiplications pending on the newer / older level (0..2) */
-    const float *tz;  /* z factor per column, 4 valid entries before [0] and up to pitch+4 */
-    const float *tx;  /* x factor per local row, valid on [-GUARD, nloc+GUARD) */
+    const float *tz;  /* z factor per column, AGUARD valid entries before [0] and up to pitch+AGUARD */
+    const float *tx;  /* x factor per local row, valid on [-AGUARD, nloc+AGUARD) */
     int tx_jlim;      /* x factor applies to columns j < tx_jlim */
     int tz_ilim;      /* z factor applies to global rows < tz_ilim */
     int tap_jlo, tap_jhi; /* some factor != 1 only if j < tap_jlo or j >= tap_jhi ... */
@@ -109,6 +114,11 @@ struct StepArgs {
     unsigned *ps_lo, *ps_hi, *ps_count;
     unsigned ps_v, ps_total;
     unsigned long long pw_timeout_ns; /* the acquire gives up (error flag 2, no update, no push) after this wall time */
+    /* multi-rectangle launch (the sponge strips of one level side by side in ONE launch instead of one short
+     * launch after the other): nrect > 0 -> a 1-D grid, CTA b belongs to the last rectangle with cta0 <= b and
+     * replaces col4_0 / ncol4 / row0 / row1 / rows_per_cta by that rectangle's */
+    int nrect;
+    struct RectGeom { int c0, c1, r0, r1, rpc, nbx, cta0; } rect[MAX_RECTS];
 };
 
 /* the few quantities that change from one time level to the next; the ordinary kernels copy
@@ -308,19 +318,33 @@ float4 add_source(const StepArgs &a, float src_amp, float4 r4, int gi, int j0)
     return make_float4(res[0], res[1], res[2], res[3]);
 }
 
+/* the z row of one thread as a flat array: zl[NB-1] .. zl[0], c4, zr[0] .. zr[NB-1] (zl[0] / zr[0] are the
+ * aligned float4 next to the centre one); the centre sample k sits at index 4*NB + k */
+template <int NB>
+FDW_HD void z_row(const float4 (&zl)[NB], const float4 c4, const float4 (&zr)[NB], float (&za)[4 * (2 * NB + 1)])
+{
+    FDW_UNROLL
+    for (int b = 0; b < NB; b++) {
+        const float4 l = zl[NB - 1 - b], r = zr[b];
+        za[4 * b + 0] = l.x; za[4 * b + 1] = l.y; za[4 * b + 2] = l.z; za[4 * b + 3] = l.w;
+        za[4 * (NB + 1 + b) + 0] = r.x; za[4 * (NB + 1 + b) + 1] = r.y; za[4 * (NB + 1 + b) + 2] = r.z; za[4 * (NB + 1 + b) + 3] = r.w;
+    }
+    za[4 * NB + 0] = c4.x; za[4 * NB + 1] = c4.y; za[4 * NB + 2] = c4.z; za[4 * NB + 3] = c4.w;
+}
+
 /* Everything of ONE ROW of one thread's float4 column once its operands are in registers: Laplacian in the
  * selected recipe, leapfrog update, source patch, trace back-injection.  w[] is the rotating x window of the
- * newer level (w[(u+io)%W] = row lr-H+io), l4 / r4 the aligned float4 left and right of the centre row, o4 the
- * older level, v4 = fl32(v2*dt2).  Shared by the global-memory kernels (step_thread) and the shared-memory tile
- * kernel (tile_thread): the arithmetic and its order exist once. */
+ * newer level (w[(u+io)%W] = row lr-H+io), zl / zr the aligned float4 blocks left and right of the centre row
+ * (one each up to order 8, two for orders 10..16), o4 the older level, v4 = fl32(v2*dt2). */
 template <int ORDER, int RECIPE, int EPI, bool PACKED>
-FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[ORDER + 1], const int u, const float4 l4,
-                         const float4 r4, const float4 o4, const float4 v4, const int gi, const int j0, const bool ring,
-                         const bool near_src)
+FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[ORDER + 1], const int u,
+                         const float4 (&zl)[zblocks(ORDER)], const float4 (&zr)[zblocks(ORDER)], const float4 o4,
+                         const float4 v4, const int gi, const int j0, const bool ring, const bool near_src)
 {
-    constexpr int H = ORDER / 2, W = ORDER + 1;
+    constexpr int H = ORDER / 2, W = ORDER + 1, NB = zblocks(ORDER), C0 = 4 * NB;
     const float4 c4 = w[(u + H) % W];
-    const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
+    float za[4 * (2 * NB + 1)];
+    z_row<NB>(zl, c4, zr, za);
     const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
     const float oo[4] = {o4.x, o4.y, o4.z, o4.w};
     const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -331,20 +355,20 @@ FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[O
             FDW_UNROLL
             for (int k = 0; k < 4; k++) {
                 if (RECIPE == RECIPE_G) {
-                    float az = fmul(za[4 + k - H], a.cz[0]);
+                    float az = fmul(za[C0 + k - H], a.cz[0]);
                     float ax = fmul(getk(w[(u + 0) % W], k), a.cx[0]);
                     FDW_UNROLL
                     for (int io = 1; io <= ORDER; io++) {
-                        az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
+                        az = fadd(az, fmul(za[C0 + k - H + io], a.cz[io]));
                         ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
                     }
                     lap[k] = fadd(az, ax);
                 } else if (RECIPE == RECIPE_C) {
-                    float acm = fmul(fmul(za[4 + k - H], a.cz[0]), a.dz2inv);
+                    float acm = fmul(fmul(za[C0 + k - H], a.cz[0]), a.dz2inv);
                     acm = fadd(acm, fmul(fmul(getk(w[(u + 0) % W], k), a.cx[0]), a.dx2inv));
                     FDW_UNROLL
                     for (int io = 1; io <= ORDER; io++) {
-                        acm = fadd(acm, fmul(fmul(za[4 + k - H + io], a.cz[io]), a.dz2inv));
+                        acm = fadd(acm, fmul(fmul(za[C0 + k - H + io], a.cz[io]), a.dz2inv));
                         acm = fadd(acm, fmul(fmul(getk(w[(u + io) % W], k), a.cx[io]), a.dx2inv));
                     }
                     lap[k] = acm;
@@ -352,7 +376,7 @@ FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[O
                     float sm = fmul(cc[k], a.cz[H] + a.cx[H]);
                     FDW_UNROLL
                     for (int d = 1; d <= H; d++) {
-                        sm = ffma(a.cz[H + d], za[4 + k - d] + za[4 + k + d], sm);
+                        sm = ffma(a.cz[H + d], za[C0 + k - d] + za[C0 + k + d], sm);
                         sm = ffma(a.cx[H + d], getk(w[(u + H - d) % W], k) + getk(w[(u + H + d) % W], k), sm);
                     }
                     lap[k] = sm;
@@ -362,7 +386,7 @@ FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[O
             /* two packed pairs per float4: points (0,1) and (2,3).  Per lane the operation
              * sequence is the scalar one of the reference, only two lanes share an instruction. */
             const f2 one = bc2(a.one);
-            constexpr int B = 4 - H; /* za index of the first z tap of point 0 */
+            constexpr int B = C0 - H; /* za index of the first z tap of point 0 */
             f2 l01, l23;
             if (RECIPE == RECIPE_G) {
                 /* two accumulators, ascending io, summed last (fd-code.cu:66-72).
@@ -409,8 +433,8 @@ FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[O
                 FDW_UNROLL
                 for (int d = 1; d <= H; d++) {
                     const float4 &wa = w[(u + H - d) % W], &wb = w[(u + H + d) % W];
-                    s0 = fma2(bc2(a.cz[H + d]), add2(pk(za[4 - d], za[5 - d]), one, pk(za[4 + d], za[5 + d])), s0);
-                    s1 = fma2(bc2(a.cz[H + d]), add2(pk(za[6 - d], za[7 - d]), one, pk(za[6 + d], za[7 + d])), s1);
+                    s0 = fma2(bc2(a.cz[H + d]), add2(pk(za[C0 - d], za[C0 + 1 - d]), one, pk(za[C0 + d], za[C0 + 1 + d])), s0);
+                    s1 = fma2(bc2(a.cz[H + d]), add2(pk(za[C0 + 2 - d], za[C0 + 3 - d]), one, pk(za[C0 + 2 + d], za[C0 + 3 + d])), s1);
                     s0 = fma2(bc2(a.cx[H + d]), add2(pk(wa.x, wa.y), one, pk(wb.x, wb.y)), s0);
                     s1 = fma2(bc2(a.cx[H + d]), add2(pk(wa.z, wa.w), one, pk(wb.z, wb.w)), s1);
                 }
@@ -458,10 +482,11 @@ FDW_HD float4 row_update(const StepArgs &a, const Level &lv, const float4 (&w)[O
 
 /* Side outputs of one row, all to global memory (aux pitch a.apitch): halo push, seismogram sample, forward
  * history, imaging.  c4 = the newer level's centre row (sponge applied as loaded), res = the new values,
- * f4 = the imaging operand of EPI_IMG_FIELD (the reconstructed source level at this point). */
+ * f4 = the imaging operand of EPI_IMG_FIELD (the reconstructed source level at this point); zfc / xonc = the z
+ * factors and the x-factor mask of this thread's own 4 columns. */
 template <int EPI, bool TAPER>
 FDW_HD void row_outputs(const StepArgs &a, const Level &lv, const float4 c4, const float4 res, const float4 f4, const int lr,
-                        const int gi, const int j0, const float *zf, const unsigned xon)
+                        const int gi, const int j0, const float *zfc, const unsigned xonc)
 {
     const long long ap = a.apitch;
     /* ---- halo push: boundary rows go to the neighbour's ghost rows over NVLink */
@@ -472,7 +497,7 @@ FDW_HD void row_outputs(const StepArgs &a, const Level &lv, const float4 c4, con
     /* ---- seismogram sample: the newer level after one more sponge pass */
     if ((EPI & EPI_RECORD) && gi >= a.rec_gi0 && gi < a.rec_gi0 + a.rec_n && a.rec_j >= j0 && a.rec_j < j0 + 4) {
         float4 s4 = c4;
-        if (TAPER) s4 = tap4(s4, zf + 4, xon >> 4, lv.tx[lr], gi < a.tz_ilim, 1);
+        if (TAPER) s4 = tap4(s4, zfc, xonc, lv.tx[lr], gi < a.tz_ilim, 1);
         a.rec[(long long)(gi - a.rec_gi0) * a.rec_nt + lv.rec_it] = getk(s4, a.rec_j - j0);
     }
     /* ---- forward history: interior rows of the newer level (sponge factor there is 1) */
@@ -500,16 +525,19 @@ FDW_HD void row_outputs(const StepArgs &a, const Level &lv, const float4 c4, con
     }
 }
 
-/* per-thread invariants of the sponge: z factors of the 12 columns j0-4 .. j0+7, x-factor column mask */
-FDW_HD bool sponge_setup(const StepArgs &a, const float *tz, int j0, float (&zf)[12], unsigned &xon)
+/* per-thread invariants of the sponge: z factors of the NZ = 4*(2*NB+1) columns j0-4*NB .. j0+4*NB+3 (the thread's
+ * own float4 and NB float4 blocks on each side), x-factor column mask */
+template <int NZ>
+FDW_HD bool sponge_setup(const StepArgs &a, const float *tz, int j0, float (&zf)[NZ], unsigned &xon)
 {
+    constexpr int C0 = (NZ - 4) / 2;
     xon = 0;
     bool zany = false; /* some z factor of these columns differs from 1 */
     FDW_UNROLL
-    for (int m = 0; m < 12; m++) {
-        zf[m] = tz[j0 - 4 + m];
+    for (int m = 0; m < NZ; m++) {
+        zf[m] = tz[j0 - C0 + m];
         zany = zany || zf[m] != 1.0f;
-        if (j0 - 4 + m < a.tx_jlim) xon |= 1u << m;
+        if (j0 - C0 + m < a.tx_jlim) xon |= 1u << m;
     }
     return zany;
 }
@@ -545,7 +573,7 @@ template <> struct Space<false> {
 template <int ORDER, int RECIPE, bool TAPER, int EPI, bool PACKED, bool TILE>
 FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const int rb, const int re)
 {
-    constexpr int H = ORDER / 2, W = ORDER + 1;
+    constexpr int H = ORDER / 2, W = ORDER + 1, NB = zblocks(ORDER), C0 = 4 * NB;
     typedef Space<TILE> S;
     typedef typename S::addr addr;
     typedef typename S::diff diff;
@@ -561,10 +589,10 @@ FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const in
     /* sponge on load.  A factor of exactly 1.0f changes nothing, so a thread whose 12 columns have no z
      * factor skips the multiplications of every row whose x factor is 1 as well: away from the sponge the
      * sponge instantiation then costs what the plain one does (it serves whole small grids). */
-    float zf[12];
+    float zf[4 * (2 * NB + 1)];
     unsigned xon = 0;
     bool zany = false;
-    if (TAPER) zany = sponge_setup(a, lv.tz, j0, zf, xon);
+    if (TAPER) zany = sponge_setup<4 * (2 * NB + 1)>(a, lv.tz, j0, zf, xon);
 
     /* ONE row cursor per thread (the centre row of the newer level); every other address of a row is the
      * cursor plus a launch-uniform byte delta, which costs an integer add from a uniform register instead
@@ -586,7 +614,7 @@ FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const in
             const int lr = rb - H + s;
             const float xf = lv.tx[lr];
             const bool zon = a.grow0 + lr < a.tz_ilim;
-            if ((zany && zon) || (xon && xf != 1.0f)) w[s] = tap4(w[s], zf + 4, xon >> 4, xf, zon, lv.np);
+            if ((zany && zon) || (xon && xf != 1.0f)) w[s] = tap4(w[s], zf + C0, xon >> C0, xf, zon, lv.np);
         }
         pc += (addr)rowb;
     }
@@ -601,27 +629,35 @@ FDW_HD void step_rows(const StepArgs &a, const Level &lv, const int j0, const in
                 const int gi = a.grow0 + lr;
                 const addr ppc = pc + (addr)d_pp;
                 float4 wn = S::ld(pc + (addr)d_in); /* row lr+H */
-                float4 l4 = S::ld(pc - 16), r4 = S::ld(pc + 16);
+                float4 zl[NB], zr[NB];
+                FDW_UNROLL
+                for (int b = 0; b < NB; b++) {
+                    zl[b] = S::ld(pc - (addr)(16 * (b + 1)));
+                    zr[b] = S::ld(pc + (addr)(16 * (b + 1)));
+                }
                 float4 o4 = S::ld(ppc);
                 const float4 v4 = S::ld_stream(pc + (addr)d_v);
                 if (TAPER) {
                     const float xf = lv.tx[lr], xfn = lv.tx[lr + H];
                     const bool zon = gi < a.tz_ilim, zonn = gi + H < a.tz_ilim;
-                    if ((zany && zonn) || (xon && xfn != 1.0f)) wn = tap4(wn, zf + 4, xon >> 4, xfn, zonn, lv.np);
+                    if ((zany && zonn) || (xon && xfn != 1.0f)) wn = tap4(wn, zf + C0, xon >> C0, xfn, zonn, lv.np);
                     if ((zany && zon) || (xon && xf != 1.0f)) {
-                        l4 = tap4(l4, zf, xon, xf, zon, lv.np);
-                        r4 = tap4(r4, zf + 8, xon >> 8, xf, zon, lv.np);
-                        o4 = tap4(o4, zf + 4, xon >> 4, xf, zon, lv.no);
+                        FDW_UNROLL
+                        for (int b = 0; b < NB; b++) {
+                            zl[b] = tap4(zl[b], zf + C0 - 4 * (b + 1), xon >> (C0 - 4 * (b + 1)), xf, zon, lv.np);
+                            zr[b] = tap4(zr[b], zf + C0 + 4 * (b + 1), xon >> (C0 + 4 * (b + 1)), xf, zon, lv.np);
+                        }
+                        o4 = tap4(o4, zf + C0, xon >> C0, xf, zon, lv.no);
                     }
                 }
                 w[(u + 2 * H) % W] = wn;
-                const float4 res = row_update<ORDER, RECIPE, EPI, PACKED>(a, lv, w, u, l4, r4, o4, v4, gi, j0, ring, near_src);
+                const float4 res = row_update<ORDER, RECIPE, EPI, PACKED>(a, lv, w, u, zl, zr, o4, v4, gi, j0, ring, near_src);
                 S::st(ppc, res);
                 if (EPI) {
                     float4 f4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if ((EPI & EPI_IMG_FIELD) && gi >= a.img_gi0 && gi < a.img_gi0 + a.img_n)
                         f4 = S::ld_stream(pc + (addr)d_f);
-                    row_outputs<EPI, TAPER>(a, lv, w[(u + H) % W], res, f4, lr, gi, j0, zf, xon);
+                    row_outputs<EPI, TAPER>(a, lv, w[(u + H) % W], res, f4, lr, gi, j0, zf + C0, xon >> C0);
                 }
                 pc += (addr)rowb;
             }
@@ -638,6 +674,35 @@ FDW_HD void step_thread(const StepArgs &a, const Level &lv, int bx, int by, int 
     const int re = rb + a.rows_per_cta < a.row1 ? rb + a.rows_per_cta : a.row1;
     if (rb >= re) return;
     step_rows<ORDER, RECIPE, TAPER, EPI, PACKED, false>(a, lv, q * 4, rb, re);
+}
+
+/* which float4 column and rows this thread owns: an ordinary 2-D launch over one rectangle, or CTA blockIdx.x
+ * of a multi-rectangle launch (StepArgs::nrect > 0); false = nothing to do */
+FDW_HD bool thread_work(const StepArgs &a, int bx, int by, int tid, int bdim, int *j0, int *rb, int *re)
+{
+    int c0 = a.col4_0, c1 = a.ncol4, r0 = a.row0, r1 = a.row1, rpc = a.rows_per_cta;
+    if (a.nrect > 0) {
+        int r = 0;
+        while (r + 1 < a.nrect && bx >= a.rect[r + 1].cta0) r++;
+        c0 = a.rect[r].c0; c1 = a.rect[r].c1; r0 = a.rect[r].r0; r1 = a.rect[r].r1; rpc = a.rect[r].rpc;
+        const int b = bx - a.rect[r].cta0, nbx = a.rect[r].nbx;
+        bx = b % nbx;
+        by = b / nbx;
+    }
+    const int q = c0 + bx * bdim + tid;
+    if (q >= c1) return false;
+    *j0 = q * 4;
+    *rb = r0 + by * rpc;
+    *re = *rb + rpc < r1 ? *rb + rpc : r1;
+    return *rb < *re;
+}
+
+/* step_thread for the kernels that may be launched over several rectangles at once (the sponge kernel) */
+template <int ORDER, int RECIPE, bool TAPER, int EPI, bool PACKED = true>
+FDW_HD void step_thread_rects(const StepArgs &a, const Level &lv, int bx, int by, int tid, int bdim)
+{
+    int j0, rb, re;
+    if (thread_work(a, bx, by, tid, bdim, &j0, &rb, &re)) step_rows<ORDER, RECIPE, TAPER, EPI, PACKED, false>(a, lv, j0, rb, re);
 }
 
 /* arguments of the shared-memory tile kernels (small grids): the grid is cut into
@@ -683,7 +748,7 @@ struct PSlabArgs {
 template <int ORDER, bool PACKED = true>
 FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, int bdim)
 {
-    constexpr int H = ORDER / 2, W = ORDER + 1;
+    constexpr int H = ORDER / 2, W = ORDER + 1, NB = zblocks(ORDER), C0 = 4 * NB;
     const int q = a.col4_0 + bx * bdim + tid;
     if (q >= a.ncol4) return;
     const int j0 = q * 4;
@@ -706,8 +771,14 @@ FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, i
             if (u < left) {
                 w[(u + 2 * H) % W] = ld4(pc);
                 const float *ctr = pc - (long long)H * pitch;
-                const float4 l4 = ld4(ctr - 4), r4 = ld4(ctr + 4), c4 = w[(u + H) % W];
-                const float za[12] = {l4.x, l4.y, l4.z, l4.w, c4.x, c4.y, c4.z, c4.w, r4.x, r4.y, r4.z, r4.w};
+                float4 zl[NB], zr[NB];
+                FDW_UNROLL
+                for (int b = 0; b < NB; b++) {
+                    zl[b] = ld4(ctr - 4 * (b + 1));
+                    zr[b] = ld4(ctr + 4 * (b + 1));
+                }
+                float za[4 * (2 * NB + 1)];
+                z_row<NB>(zl, w[(u + H) % W], zr, za);
                 float res[4];
                 if (!PACKED) {
                     FDW_UNROLL
@@ -715,7 +786,7 @@ FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, i
                         float az = 0.0f, ax = 0.0f;
                         FDW_UNROLL
                         for (int io = 0; io <= ORDER; io++) {
-                            az = fadd(az, fmul(za[4 + k - H + io], a.cz[io]));
+                            az = fadd(az, fmul(za[C0 + k - H + io], a.cz[io]));
                             ax = fadd(ax, fmul(getk(w[(u + io) % W], k), a.cx[io]));
                         }
                         res[k] = fadd(az, ax);
@@ -724,7 +795,7 @@ FDW_HD void lap_thread(const StepArgs &a, float *lap, int bx, int by, int tid, i
                     /* packed pairs (0,1), (2,3); every lane runs the reference's scalar sequence,
                      * including the leading "0 +" adds (fd-source-code.cu:121-131) */
                     const f2 one = bc2(a.one);
-                    constexpr int B = 4 - H;
+                    constexpr int B = C0 - H;
                     f2 az0 = bc2(0.0f), az1 = bc2(0.0f), ax0 = bc2(0.0f), ax1 = bc2(0.0f);
                     FDW_UNROLL
                     for (int io = 0; io <= ORDER; io++) {

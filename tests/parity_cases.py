@@ -137,7 +137,7 @@ def case_advance(lib, family, recipe, taper, order=8, nx=37, nz=29, nxb=9, nzb=8
 
 
 # ------------------------------------------------------------------ GPU-family RTM shot
-def case_gpu_rtm(lib, nx=41, nz=33, nxb=8, nzb=8, nt=60, compat=True, seed=5, host_roundtrip=False):
+def case_gpu_rtm(lib, nx=41, nz=33, nxb=8, nzb=8, nt=60, compat=True, seed=5, host_roundtrip=False, order=8):
     rng = np.random.default_rng(seed)
     nxe, nze = nx + 2 * nxb, nz + 2 * nzb
     dx = dz = 10.0
@@ -146,10 +146,10 @@ def case_gpu_rtm(lib, nx=41, nz=33, nxb=8, nzb=8, nt=60, compat=True, seed=5, ho
     srce = O.ricker_wavelet(nt, dt, fpeak, O.FAM_G)
     sx, sz, gz = nxb + nx // 3, nzb, nzb
     dobs = rng.uniform(-1, 1, (nx, nt)).astype(np.float32)
-    cfg = O.GpuCfg(8, nxe, nze, nxb, nzb, nt, dx, dz, dt, fac, int(compat))
+    cfg = O.GpuCfg(order, nxe, nze, nxb, nzb, nt, dx, dz, dt, fac, int(compat))
     P, PP = O.gpu_forward(cfg, v2, srce, sx, sz)
     im = O.gpu_back(cfg, P, PP, v2, dobs, gz)
-    with Wave2D(nx, nz, nxb, nzb, dx, dz, dt, order=8, fac=fac, family=FAMILY_GPU, taper=TAPER_TOP,
+    with Wave2D(nx, nz, nxb, nzb, dx, dz, dt, order=order, fac=fac, family=FAMILY_GPU, taper=TAPER_TOP,
                 compat_extents=compat, nt=nt, lib=lib) as w:
         w.set_v2(v2)
         w.set_wavelet(srce)
@@ -183,16 +183,16 @@ def case_mod_shot(lib, nx=33, nz=27, nxb=7, nzb=6, nt=50, seed=9, order=8):
     assert_bit_equal(got, want, "mod_main seismogram")
 
 
-def case_rtm_shot_cpu(lib, nx=31, nz=31, nxb=7, nzb=7, nt=40, ns=2, is_=0, seed=11):
+def case_rtm_shot_cpu(lib, nx=31, nz=31, nxb=7, nzb=7, nt=40, ns=2, is_=0, seed=11, order=8):
     rng = np.random.default_rng(seed)
     dx, dz, dt, fac, fpeak = 10.0, 10.0, 0.001, 0.05, 35.0
     v2 = layered_v2(nx, nz, nxb, nzb, rng)
     srce = O.ricker_wavelet(nt, dt, fpeak, O.FAM_C)
     sx, sz, gz = nxb + 5, nzb, nzb
     dobs = rng.uniform(-1, 1, (ns, nx, nt)).astype(np.float32)
-    cfg = O.CpuCfg(8, nx, nz, nxb, nzb, nt, dx, dz, dt, fac)
+    cfg = O.CpuCfg(order, nx, nz, nxb, nzb, nt, dx, dz, dt, fac)
     want = O.rtm_shot(cfg, v2, srce, sx, sz, gz, dobs, is_)
-    with Wave2D(nx, nz, nxb, nzb, dx, dz, dt, order=8, fac=fac, family=FAMILY_CPU, taper=TAPER_TOP, nt=nt,
+    with Wave2D(nx, nz, nxb, nzb, dx, dz, dt, order=order, fac=fac, family=FAMILY_CPU, taper=TAPER_TOP, nt=nt,
                 history=True, lib=lib) as w:
         w.set_v2(v2)
         w.set_wavelet(srce)

@@ -23,8 +23,14 @@ def test_bad_arguments_are_reported_not_crashed(emu):
         Wave2D(0, 10, 2, 2, 10.0, 10.0, 0.001, lib=emu)
     assert e.value.code == -1 and "bad grid" in str(e.value)
     with pytest.raises(FdwError) as e:
-        Wave2D(16, 16, 4, 4, 10.0, 10.0, 0.001, order=10, lib=emu)  # host tables support it, the device does not
+        Wave2D(16, 16, 4, 4, 10.0, 10.0, 0.001, order=18, lib=emu)  # host tables support it, the device stops at 16
     assert e.value.code == -6
+    with pytest.raises(FdwError) as e:
+        Wave2D(16, 16, 4, 4, 10.0, 10.0, 0.001, order=7, lib=emu)
+    assert e.value.code == -6
+    with pytest.raises(FdwError) as e:  # slabs exchange 4 ghost rows: orders above 8 need the whole grid
+        Wave2D(40, 16, 4, 4, 10.0, 10.0, 0.001, order=12, slab=(0, 24), lib=emu)
+    assert e.value.code == -6 and "ghost rows" in str(e.value)
     with pytest.raises(FdwError) as e:
         Wave2D(16, 16, 4, 4, 10.0, 10.0, 0.001, slab=(5, 400), lib=emu)
     assert e.value.code == -1

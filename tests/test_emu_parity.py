@@ -1,6 +1,7 @@
 """CPU-only: libfdwave's host logic and kernel bodies (host build against the
 fake CUDA runtime in tests/emu/) vs the oracle.  The GPU tests run the same
 cases through the real library (test_gpu_parity.py)."""
+import numpy as np
 import pytest
 
 import parity_cases as PC
@@ -26,7 +27,7 @@ def launch_mode(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("order", [2, 4, 6, 8])
+@pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16])
 @pytest.mark.parametrize("shape", [(61, 47), (40, 64), (9, 9), (300, 130)])
 def test_stencil(emu, order, shape):
     PC.case_stencil(emu, order, shape)
@@ -36,7 +37,7 @@ def test_stencil_golden(emu, golden_dir):
     PC.case_stencil_golden(emu, golden_dir)
 
 
-@pytest.mark.parametrize("order", [2, 4, 6, 8])
+@pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16])
 @pytest.mark.parametrize("family,recipe,taper,src", [
     (FAMILY_GPU, RECIPE_G, TAPER_TOP, SRC_POINT),
     (FAMILY_GPU, RECIPE_G, TAPER_NONE, SRC_POINT),
@@ -91,3 +92,32 @@ def test_mod_main_shot(emu, launch_mode):
 @pytest.mark.parametrize("is_", [0, 1])
 def test_rtm_main_shot(emu, launch_mode, is_):
     PC.case_rtm_shot_cpu(emu, is_=is_)
+
+
+@pytest.mark.parametrize("multirect", ["1", "0"])
+def test_sponge_strips_share_one_launch(emu, multirect, monkeypatch):
+    """a four-sided sponge on a grid that is not "small": bulk + 4 strips per level; the strips go out as ONE
+    multi-rectangle launch (2 launches per level) unless FDW_MULTIRECT=0 (5 per level) -- same bits either way"""
+    from parallel_finite_difference_computation_b200 import Wave2D
+    monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
+    monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+    monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    monkeypatch.setenv("FDW_MULTIRECT", multirect)
+    PC.case_advance(emu, FAMILY_CPU, RECIPE_C, TAPER_FOUR, nx=70, nz=300, nxb=12, nzb=10, nt=6, src_kind=SRC_GAUSS7)
+    with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=emu) as w:
+        w.set_v2(np.full((94, 320), 4.0e6, np.float32))
+        w.zero()
+        n0 = w.launch_count()
+        w.advance(0, 4)
+        # level 0 has no sponge pass pending yet (CPU family: update, then sponge): one launch
+        assert w.launch_count() - n0 == (1 + 3 * 2 if multirect == "1" else 1 + 3 * 5)
+
+
+@pytest.mark.parametrize("order", [10, 12, 16])
+def test_shots_above_order_8(emu, order):
+    """the reference's windowed-sinc weights (functions.c:119-157 makeo2) drive the same kernels at
+    orders 10..16 -- whole shots of both families (forward + backward + imaging, modelling, RTM with history)"""
+    PC.case_gpu_rtm(emu, compat=False, order=order)
+    PC.case_gpu_rtm(emu, compat=True, host_roundtrip=True, order=order)
+    PC.case_mod_shot(emu, order=order)
+    PC.case_rtm_shot_cpu(emu, order=order)

@@ -23,7 +23,7 @@ def lib():
     return L
 
 
-@pytest.mark.parametrize("order", [2, 4, 6, 8])
+@pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16])
 @pytest.mark.parametrize("shape", [(61, 47), (40, 64), (9, 9), (300, 130), (1030, 2052)])
 def test_stencil(lib, order, shape):
     PC.case_stencil(lib, order, shape)
@@ -47,7 +47,7 @@ def launch_mode(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("order", [2, 4, 6, 8])
+@pytest.mark.parametrize("order", [2, 4, 6, 8, 10, 12, 14, 16])
 @pytest.mark.parametrize("family,recipe,taper,src", [
     (FAMILY_GPU, RECIPE_G, TAPER_TOP, SRC_POINT),
     (FAMILY_GPU, RECIPE_G, TAPER_NONE, SRC_POINT),
@@ -107,6 +107,35 @@ def test_mod_main_shot(lib, launch_mode):
 @pytest.mark.parametrize("is_", [0, 1])
 def test_rtm_main_shot(lib, launch_mode, is_):
     PC.case_rtm_shot_cpu(lib, is_=is_)
+
+
+@pytest.mark.parametrize("multirect", ["1", "0"])
+def test_sponge_strips_share_one_launch(lib, multirect, monkeypatch):
+    """a four-sided sponge on a grid that is not "small": bulk + 4 strips per level; the strips go out as ONE
+    multi-rectangle launch (2 launches per level) unless FDW_MULTIRECT=0 (5 per level) -- same bits either way"""
+    from parallel_finite_difference_computation_b200 import Wave2D
+    monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
+    monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+    monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    monkeypatch.setenv("FDW_MULTIRECT", multirect)
+    PC.case_advance(lib, FAMILY_CPU, RECIPE_C, TAPER_FOUR, nx=70, nz=300, nxb=12, nzb=10, nt=6, src_kind=SRC_GAUSS7)
+    with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=lib) as w:
+        w.set_v2(np.full((94, 320), 4.0e6, np.float32))
+        w.zero()
+        n0 = w.launch_count()
+        w.advance(0, 4)
+        # level 0 has no sponge pass pending yet (CPU family: update, then sponge): one launch
+        assert w.launch_count() - n0 == (1 + 3 * 2 if multirect == "1" else 1 + 3 * 5)
+
+
+@pytest.mark.parametrize("order", [10, 12, 16])
+def test_shots_above_order_8(lib, order):
+    """the reference's windowed-sinc weights (functions.c:119-157 makeo2) drive the same kernels at
+    orders 10..16 -- whole shots of both families (forward + backward + imaging, modelling, RTM with history)"""
+    PC.case_gpu_rtm(lib, compat=False, order=order)
+    PC.case_gpu_rtm(lib, compat=True, host_roundtrip=True, order=order)
+    PC.case_mod_shot(lib, order=order)
+    PC.case_rtm_shot_cpu(lib, order=order)
 
 
 def test_tile_kernel_runs_whole_phases(lib):
