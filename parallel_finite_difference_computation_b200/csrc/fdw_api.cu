@@ -157,6 +157,11 @@ struct fdw_ctx {
     int use_graph = 1;
     long long graph_replays = 0;
     int use_multirect = 1;       /* the sponge strips of a level in ONE launch (FDW_MULTIRECT=0: one launch per strip) */
+    /* single-GPU level loop as a replayed CUDA graph (pairs of levels, node arguments refreshed): grids whose level
+     * is tens of microseconds -- above the tile / persistent kernels' range, below the size where two stream-ordered
+     * launches, two event records and two waits per level no longer matter (FDW_LEVEL_GRAPH=0 turns it off) */
+    int level_graph = 1;
+    long long level_graph_limit = 1LL << 25; /* float4 columns x rows */
     /* split-phase step (slab decomposition) */
     bool step_open = false;
     StepArgs step_args;
@@ -348,7 +353,66 @@ static int cached_occupancy(const void *kern, int nthreads)
     return occ;
 }
 
-static double g_fill_waves = 2.0; /* FDW_FILL_WAVES */
+/* Rows per CTA of a launch that does not fill the machine many times over.  Such a launch is a latency chain: a
+ * CTA loads its 8-row x window, then takes one dependent memory round trip per row, and the launch lasts as many
+ * of those chains as it has waves of resident CTAs -- cost(rpc) = max(1, CTAs(rpc) / resident CTAs) x (8 + rpc),
+ * minimised over rpc = 2..7.  Large grids get 7 (the measured optimum of the HBM-bound regime), launches below
+ * one wave get 2 (shortest chain), and the sponge strips of a mid-size grid -- a few thousand CTAs -- get the
+ * chunking that keeps them to about one wave (measured on the 8272 x 2128 grid: strips at 2 rows per CTA take 20 us
+ * each in 1.5 waves; profiles/r02l_level_sweep.log).  nrect rectangles of one launch are chunked together. */
+static int g_rpc_rule = 1; /* FDW_RPC_RULE=0: the earlier rule (halve 7 -> 4 -> 2 until the grid fills the machine twice) */
+/* fold[i] (optional): row chunks one CTA of rectangle i holds side by side (StepArgs::rect[].lw) */
+static int pick_rows_per_cta(long long cap, const int *gx, const int *rows, int nrect, const int *fold = nullptr)
+{
+    auto ctas_of = [&](int i, int rpc) {
+        const int chunks = (rows[i] + rpc - 1) / rpc, f = fold ? fold[i] : 1;
+        return (long long)gx[i] * ((chunks + f - 1) / f);
+    };
+    if (!g_rpc_rule) {
+        int rpc = FDW_CTA_ROWS;
+        long long ctas;
+        do {
+            ctas = 0;
+            for (int i = 0; i < nrect; i++) ctas += ctas_of(i, rpc);
+            if (rpc <= 2 || ctas >= 2 * cap) break;
+            rpc = (rpc + 1) / 2;
+        } while (true);
+        return rpc;
+    }
+    /* a few waves (mid-size grids, e.g. 8272 x 2128 = 4.2 waves of 7-row CTAs): a nearly empty last wave costs a whole
+     * CTA lifetime at low occupancy -- among 5 / 6 / 7 rows take the chunking whose last wave is fullest, weighed
+     * against the halo rows a shorter chunk re-reads (measured on that grid: 7 rows 63.6 us per level, 6 rows
+     * 61.7, 5 rows 61.7; profiles/r02m_c5_grid_level_sweep_folded_strips.log) */
+    {
+        long long c7 = 0;
+        for (int i = 0; i < nrect; i++) c7 += ctas_of(i, FDW_CTA_ROWS);
+        const double w7 = (double)c7 / (double)cap;
+        if (w7 > 1.5 && w7 < 12.0) {
+            int best = FDW_CTA_ROWS;
+            double best_eff = -1.0;
+            for (int rpc = FDW_CTA_ROWS; rpc >= 5; rpc--) {
+                long long ctas = 0;
+                for (int i = 0; i < nrect; i++) ctas += ctas_of(i, rpc);
+                const double w = (double)ctas / (double)cap;
+                const double eff = w / (double)(long long)(w + 0.999999) * rpc / (rpc + 1.0);
+                if (eff > best_eff + 0.01) { best_eff = eff; best = rpc; }
+            }
+            return best;
+        }
+        if (w7 >= 12.0) return FDW_CTA_ROWS;
+    }
+    int best = FDW_CTA_ROWS;
+    double best_cost = -1.0;
+    for (int rpc = FDW_CTA_ROWS; rpc >= 2; rpc--) {
+        long long ctas = 0;
+        for (int i = 0; i < nrect; i++) ctas += ctas_of(i, rpc);
+        const double waves = (double)ctas / (double)cap;
+        const double cost = (waves > 1.0 ? waves : 1.0) * (8 + rpc);
+        if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best = rpc; }
+    }
+    return best;
+}
+
 static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int thr_override, int rpc_override,
                             dim3 *grid, dim3 *block, int *rows_per_cta)
 {
@@ -357,13 +421,8 @@ static void launch_geometry(const void *kern, int nsm, int ncols, int rows, int 
     if (nthreads < 32) nthreads = 32;
     int gx = (ncols + nthreads - 1) / nthreads;
     int rpc = FDW_CTA_ROWS;
-    if (rpc_override > 0) {
-        rpc = rpc_override;
-    } else {
-        const long long cap = (long long)nsm * cached_occupancy(kern, nthreads);
-        /* small problems: shorten the chunks until the grid fills the machine twice over */
-        while (rpc > 2 && (double)gx * ((rows + rpc - 1) / rpc) < g_fill_waves * (double)cap) rpc = (rpc + 1) / 2;
-    }
+    if (rpc_override > 0) rpc = rpc_override;
+    else rpc = pick_rows_per_cta((long long)nsm * cached_occupancy(kern, nthreads), &gx, &rows, 1);
     while ((rows + rpc - 1) / rpc > 65535) rpc *= 2; /* gridDim.y limit */
     int gy = (rows + rpc - 1) / rpc;
     *grid = dim3(gx, gy < 1 ? 1 : gy, 1);
@@ -449,8 +508,8 @@ static int launch_rects(fdw_ctx *c, const StepArgs &base, int recipe, int epi, c
     if (!k || n > (int)fdw::MAX_RECTS) return FDW_ERR_UNSUPPORTED;
     StepArgs a = base;
     a.nrect = 0;
-    long long total = 0;
     unsigned threads = 0;
+    int gxs[fdw::MAX_RECTS], rws[fdw::MAX_RECTS], folds[fdw::MAX_RECTS];
     for (int i = 0; i < n; i++) {
         if (rc[i].c1 <= rc[i].c0 || rc[i].r1 <= rc[i].r0) continue;
         if (!rc[i].sponge) return FDW_ERR_UNSUPPORTED;
@@ -460,12 +519,31 @@ static int launch_rects(fdw_ctx *c, const StepArgs &base, int recipe, int epi, c
                         &grid, &block, &rpc);
         if (threads && block.x != threads) return FDW_ERR_UNSUPPORTED;
         threads = block.x;
-        StepArgs::RectGeom &g = a.rect[a.nrect++];
-        g.c0 = rc[i].c0; g.c1 = rc[i].c1; g.r0 = rc[i].r0; g.r1 = rc[i].r1; g.rpc = rpc; g.nbx = (int)grid.x;
-        g.cta0 = (int)total;
-        total += (long long)grid.x * grid.y;
+        /* lanes side by side in z: the fold that pads the rectangle's width least (ties: the wider) */
+        const int ncols = rc[i].c1 - rc[i].c0;
+        int lw = (int)threads;
+        for (int w = (int)threads / 2; w >= 8 && threads % w == 0; w /= 2)
+            if ((ncols + w - 1) / w * w < (ncols + lw - 1) / lw * lw) lw = w;
+        StepArgs::RectGeom &g = a.rect[a.nrect];
+        g.c0 = rc[i].c0; g.c1 = rc[i].c1; g.r0 = rc[i].r0; g.r1 = rc[i].r1; g.rpc = rpc; g.lw = lw;
+        g.nbx = (ncols + lw - 1) / lw;
+        gxs[a.nrect] = g.nbx; rws[a.nrect] = rc[i].r1 - rc[i].r0; folds[a.nrect] = (int)threads / lw;
+        a.nrect++;
     }
-    if (a.nrect < 2 || total > 0x7fffffffLL) return FDW_ERR_UNSUPPORTED;
+    if (a.nrect < 1) return FDW_ERR_UNSUPPORTED;
+    /* the rectangles share the machine: one chunking for all of them */
+    const int rpc_all = c->rows_per_cta_override > 0
+                            ? c->rows_per_cta_override
+                            : pick_rows_per_cta((long long)c->nsm * cached_occupancy(k, (int)threads), gxs, rws, a.nrect, folds);
+    long long total = 0;
+    for (int i = 0; i < a.nrect; i++) {
+        StepArgs::RectGeom &g = a.rect[i];
+        const int fold = (int)threads / g.lw, chunks = (g.r1 - g.r0 + rpc_all - 1) / rpc_all;
+        g.rpc = rpc_all;
+        g.cta0 = (int)total;
+        total += (long long)g.nbx * ((chunks + fold - 1) / fold);
+    }
+    if (total > 0x7fffffffLL) return FDW_ERR_UNSUPPORTED;
     a.col4_0 = a.rect[0].c0; a.ncol4 = a.rect[0].c1; a.row0 = a.rect[0].r0; a.row1 = a.rect[0].r1; a.rows_per_cta = a.rect[0].rpc;
     const dim3 grid((unsigned)total, 1, 1), block(threads, 1, 1);
     c->launches++;
@@ -532,8 +610,11 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
          * sponge, in whole warps */
         const int zr = H > 4 ? 8 : 4;
         int cs = 0, cb = nc;
-        if (c->tap_jlo > INT_MIN) cs = (((c->tap_jlo + zr + 3) / 4) + 31) / 32 * 32;
-        if (c->tap_jhi < INT_MAX) cb = ((c->tap_jhi - 3 - zr > 0 ? c->tap_jhi - 3 - zr : 0) / 4) / 32 * 32;
+        /* (strip launches fold their CTAs down to 8 lanes in z, see StepArgs::rect; the bulk's warps then start on a
+         * 128-byte line all the same) */
+        const int gran = c->use_multirect ? 8 : 32;
+        if (c->tap_jlo > INT_MIN) cs = (((c->tap_jlo + zr + 3) / 4) + gran - 1) / gran * gran;
+        if (c->tap_jhi < INT_MAX) cb = ((c->tap_jhi - 3 - zr > 0 ? c->tap_jhi - 3 - zr : 0) / 4) / gran * gran;
         if (cs > nc) cs = nc;
         if (cb < cs) cb = cs;
         /* rows whose x window touches an x sponge that applies to every column */
@@ -558,7 +639,7 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
         CU(cudaStreamWaitEvent(ss, c->ev_fork, 0));
     }
     if (c->rec && do_fork) c->rec_lane = 2;
-    if (c->use_multirect && nside > 1) {
+    if (c->use_multirect && nside > 0) {
         const int rc = launch_rects(c, base, recipe, epi, side, nside, ss);
         if (rc == FDW_OK) nside = 0; /* all strips are in flight */
         else if (rc != FDW_ERR_UNSUPPORTED) { c->rec_lane = -1; return rc; }
@@ -821,7 +902,10 @@ static int try_persistent(fdw_ctx *c, int recipe, int epi, bool sponge, bool sou
     return 1;
 }
 
-/* n levels of pair 0: one persistent launch when the grid is small, else one launch per level */
+static int graph_submit(fdw_ctx *c, std::vector<RecLaunch> &rec);
+
+/* n levels of pair 0: one persistent launch when the grid is small, a replayed graph of two levels when it is
+ * mid-size, else one launch (plus strips) per level */
 template <class FillStatic, class FillLevel>
 static int run_levels(fdw_ctx *c, int recipe, int epi, bool sponge, bool source, int it0, int n, int tidx_cpu,
                       FillStatic fill_static, FillLevel fill_level)
@@ -829,7 +913,23 @@ static int run_levels(fdw_ctx *c, int recipe, int epi, bool sponge, bool source,
     int rc;
     if (try_tile(c, recipe, epi, sponge, source, it0, n, tidx_cpu, fill_static)) return FDW_OK;
     if (try_persistent(c, recipe, epi, sponge, source, it0, n, tidx_cpu, fill_static, &rc)) return rc;
-    for (int it = it0; it < it0 + n; it++)
+    int it = it0;
+    if (c->use_graph && c->level_graph && !c->step_open && !c->rec && n >= 4 &&
+        (long long)c->ncol4 * c->nloc < c->level_graph_limit) {
+        for (; it + 1 < it0 + n; it += 2) {
+            std::vector<RecLaunch> rec;
+            c->rec = &rec;
+            rc = FDW_OK;
+            for (int l = 0; l < 2 && rc == FDW_OK; l++) {
+                c->rec_level = l;
+                rc = step_pair(c, 0, recipe, epi, sponge, source, it + l, [&](StepArgs &a) { fill_level(a, it + l); });
+            }
+            c->rec = nullptr;
+            CHECK(rc);
+            CHECK(graph_submit(c, rec));
+        }
+    }
+    for (; it < it0 + n; it++)
         CHECK(step_pair(c, 0, recipe, epi, sponge, source, it, [&](StepArgs &a) { fill_level(a, it); }));
     return FDW_OK;
 }
@@ -1014,8 +1114,10 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_PSLAB_LIMIT")) c->pslab_limit = atoll(e);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
-    if (const char *e = getenv("FDW_FILL_WAVES")) g_fill_waves = atof(e);
+    if (const char *e = getenv("FDW_RPC_RULE")) g_rpc_rule = atoi(e);
     if (const char *e = getenv("FDW_MULTIRECT")) c->use_multirect = atoi(e);
+    if (const char *e = getenv("FDW_LEVEL_GRAPH")) c->level_graph = atoi(e);
+    if (const char *e = getenv("FDW_LEVEL_GRAPH_LIMIT")) c->level_graph_limit = atoll(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
     if (const char *e = getenv("FDW_FUSE_FLAGS")) c->fuse_flags = atoi(e);
     if (const char *e = getenv("FDW_TIMEOUT_MS")) c->timeout_ns = 1000000ull * (unsigned long long)atoll(e);
@@ -2131,6 +2233,14 @@ static int peer_level_pair_graph(fdw_ctx *c, int it)
     for (int l = 0; l < 2 && rc == FDW_OK; l++) { c->rec_level = l; rc = peer_level(c, it + l); }
     c->rec = nullptr;
     CHECK(rc);
+    return graph_submit(c, rec);
+}
+
+/* build the graph of a recorded launch list, or -- same kernels, lanes and grids as the last one -- refresh the
+ * node arguments of the instantiated graph; launch it */
+static int graph_submit(fdw_ctx *c, std::vector<RecLaunch> &rec)
+{
+    if (rec.empty()) return FDW_OK;
     if (!c->lexec || !same_shape(rec, c->lshape)) {
         CHECK(graph_build(c, rec));
     } else {

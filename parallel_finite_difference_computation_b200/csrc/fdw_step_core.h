@@ -116,9 +116,11 @@ struct StepArgs {
     unsigned long long pw_timeout_ns; /* the acquire gives up (error flag 2, no update, no push) after this wall time */
     /* multi-rectangle launch (the sponge strips of one level side by side in ONE launch instead of one short
      * launch after the other): nrect > 0 -> a 1-D grid, CTA b belongs to the last rectangle with cta0 <= b and
-     * replaces col4_0 / ncol4 / row0 / row1 / rows_per_cta by that rectangle's */
+     * replaces col4_0 / ncol4 / row0 / row1 / rows_per_cta by that rectangle's.  A rectangle narrower than a
+     * warp folds the CTA: lw = 8 / 16 / 32 lanes side by side in z, blockDim/lw row chunks per CTA (a z sponge of
+     * 40 columns then costs a 64-column strip of the slow sponge instantiation instead of a 128-column one). */
     int nrect;
-    struct RectGeom { int c0, c1, r0, r1, rpc, nbx, cta0; } rect[MAX_RECTS];
+    struct RectGeom { int c0, c1, r0, r1, rpc, nbx, cta0, lw; } rect[MAX_RECTS];
 };
 
 /* the few quantities that change from one time level to the next; the ordinary kernels copy
@@ -685,9 +687,11 @@ FDW_HD bool thread_work(const StepArgs &a, int bx, int by, int tid, int bdim, in
         int r = 0;
         while (r + 1 < a.nrect && bx >= a.rect[r + 1].cta0) r++;
         c0 = a.rect[r].c0; c1 = a.rect[r].c1; r0 = a.rect[r].r0; r1 = a.rect[r].r1; rpc = a.rect[r].rpc;
-        const int b = bx - a.rect[r].cta0, nbx = a.rect[r].nbx;
+        const int b = bx - a.rect[r].cta0, nbx = a.rect[r].nbx, lw = a.rect[r].lw;
         bx = b % nbx;
-        by = b / nbx;
+        by = (b / nbx) * (bdim / lw) + tid / lw;
+        tid %= lw;
+        bdim = lw;
     }
     const int q = c0 + bx * bdim + tid;
     if (q >= c1) return false;

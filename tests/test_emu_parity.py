@@ -15,15 +15,18 @@ def emu():
     return load_emu()
 
 
-@pytest.fixture(params=["persistent", "one-launch", "rectangles", "rectangles+fork"])
+@pytest.fixture(params=["persistent", "one-launch", "rectangles", "rectangles+fork", "level-graph"])
 def launch_mode(request, monkeypatch):
     """the library picks one sponge-kernel launch for tiny grids and plain/sponge rectangles
-    (optionally forked to a side stream) for large ones; force each path on the small test grids"""
+    (optionally forked to a side stream) for large ones, issued directly or -- mid-size grids -- as a replayed CUDA
+    graph of two levels; force each path on the small test grids"""
     if request.param != "persistent":
         monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")  # one launch per level
     if request.param not in ("one-launch", "persistent"):
         monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
-        monkeypatch.setenv("FDW_FORK_LIMIT", "0" if request.param.endswith("fork") else str(1 << 40))
+        monkeypatch.setenv("FDW_FORK_LIMIT", "0" if request.param != "rectangles" else str(1 << 40))
+    if request.param != "level-graph":
+        monkeypatch.setenv("FDW_LEVEL_GRAPH", "0")
     return request.param
 
 
@@ -92,6 +95,26 @@ def test_mod_main_shot(emu, launch_mode):
 @pytest.mark.parametrize("is_", [0, 1])
 def test_rtm_main_shot(emu, launch_mode, is_):
     PC.case_rtm_shot_cpu(emu, is_=is_)
+
+
+def test_level_loop_is_a_replayed_graph(emu, monkeypatch):
+    """a grid above the tile / persistent range: pairs of levels go out as one replayed CUDA graph (arguments
+    refreshed per pair), the odd last level directly; bit-exact like every other path (launch_mode level-graph)"""
+    from parallel_finite_difference_computation_b200 import Wave2D
+    monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
+    monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+    monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=emu) as w:
+        w.set_v2(np.full((94, 320), 4.0e6, np.float32))
+        w.zero()
+        w.advance(0, 9)
+        assert w.graph_replays() == 4
+    monkeypatch.setenv("FDW_LEVEL_GRAPH", "0")
+    with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=emu) as w:
+        w.set_v2(np.full((94, 320), 4.0e6, np.float32))
+        w.zero()
+        w.advance(0, 9)
+        assert w.graph_replays() == 0
 
 
 @pytest.mark.parametrize("multirect", ["1", "0"])

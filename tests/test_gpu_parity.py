@@ -33,10 +33,11 @@ def test_stencil_golden_output_teste(lib, golden_dir):
     PC.case_stencil_golden(lib, golden_dir)
 
 
-@pytest.fixture(params=["tile", "persistent", "one-launch", "rectangles+fork"])
+@pytest.fixture(params=["tile", "persistent", "one-launch", "rectangles+fork", "level-graph"])
 def launch_mode(request, monkeypatch):
     # tile: the default for small grids (shared-memory tiles, one cooperative launch per phase);
-    # persistent: round 1's L2-resident kernel; the others: one (or several) launches per level
+    # persistent: round 1's L2-resident kernel; the others: one (or several) launches per level, issued directly or
+    # (level-graph: what mid-size grids get) as a replayed CUDA graph of two levels
     if request.param == "persistent":
         monkeypatch.setenv("FDW_TILE", "0")
     if request.param not in ("persistent", "tile"):
@@ -44,6 +45,8 @@ def launch_mode(request, monkeypatch):
     if request.param not in ("one-launch", "persistent", "tile"):
         monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
         monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    if request.param != "level-graph":
+        monkeypatch.setenv("FDW_LEVEL_GRAPH", "0")
     return request.param
 
 
@@ -107,6 +110,26 @@ def test_mod_main_shot(lib, launch_mode):
 @pytest.mark.parametrize("is_", [0, 1])
 def test_rtm_main_shot(lib, launch_mode, is_):
     PC.case_rtm_shot_cpu(lib, is_=is_)
+
+
+def test_level_loop_is_a_replayed_graph(lib, monkeypatch):
+    """a grid above the tile / persistent range: pairs of levels go out as one replayed CUDA graph (arguments
+    refreshed per pair), the odd last level directly; bit-exact like every other path (launch_mode level-graph)"""
+    from parallel_finite_difference_computation_b200 import Wave2D
+    monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
+    monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+    monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=lib) as w:
+        w.set_v2(np.full((94, 320), 4.0e6, np.float32))
+        w.zero()
+        w.advance(0, 9)
+        assert w.graph_replays() == 4
+    monkeypatch.setenv("FDW_LEVEL_GRAPH", "0")
+    with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=lib) as w:
+        w.set_v2(np.full((94, 320), 4.0e6, np.float32))
+        w.zero()
+        w.advance(0, 9)
+        assert w.graph_replays() == 0
 
 
 @pytest.mark.parametrize("multirect", ["1", "0"])
