@@ -28,25 +28,21 @@ static float *xalloc(size_t n)
     return p;
 }
 
-/* like the reference: a short read leaves the rest of the (zeroed) buffer untouched */
+/* raw float32 files: the library's readers / writers (fdw_read_floats / fdw_write_floats, csrc/fdw_host.c).
+ * Like the reference, a short read leaves the rest of the (zeroed) buffer untouched. */
 static size_t read_floats(const char *path, float *dst, size_t n, int must_exist)
 {
-    FILE *f = fopen(path, "rb");
-    if (!f) {
+    const long long got = fdw_read_floats(path, dst, (long long)n);
+    if (got < 0) {
         if (must_exist) DIE("cannot open %s", path);
         return 0;
     }
-    size_t got = fread(dst, sizeof(float), n, f);
-    fclose(f);
-    return got;
+    return (size_t)got;
 }
 
 static void write_floats(const char *path, const float *src, size_t n, const char *mode)
 {
-    FILE *f = fopen(path, mode);
-    if (!f) DIE("cannot open %s for writing", path);
-    if (fwrite(src, sizeof(float), n, f) != n) DIE("short write to %s", path);
-    fclose(f);
+    if (fdw_write_floats(path, src, (long long)n, mode[0] == 'a') != FDW_OK) DIE("%s", fdw_last_error());
 }
 
 static double now_s(void)

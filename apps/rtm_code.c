@@ -69,7 +69,6 @@ int main(int argc, char **argv)
         if (f) fclose(f);
     }
     float *imloc = xalloc(ni), *img = xalloc(ni), *img_lap = xalloc(ni);
-    FILE *fnum = fopen("image.num", "w");
     double t_dev = 0;
     for (int is = 0; is < ns; is++) {
         const int sx = in.fsx + is * in.ds + nxb;
@@ -87,14 +86,8 @@ int main(int argc, char **argv)
         FDW(fdw_backward(ctx, NULL, NULL, d_obs + (size_t)is * ntr, gz, imloc));
         t_dev += now_s() - t0;
         fprintf(stdout, "\n");
-        if (fnum) fprintf(fnum, "======== %i ========\n", is);
-        for (int iz = 0; iz < nz; iz++)
-            for (int ix = 0; ix < nx; ix++) {
-                img[(size_t)ix * nz + iz] += imloc[(size_t)ix * nz + iz];
-                if (fnum) fprintf(fnum, " %f \n", img[(size_t)ix * nz + iz]);
-            }
+        FDW(fdw_image_stack_shot("image.num", is, nx, nz, img, imloc)); /* img += imloc + the text dump, fd-code.cu:521-528 */
     }
-    if (fnum) fclose(fnum);
     printf("> Exec time = %.2f (s)\n", (double)(long)(now_s() - t_start)); /* whole seconds, like fd-code.cu:536 */
     fprintf(stderr, "[fdwave] %d shot(s), %d steps each: %.3f s in forward+backward (%.2f Gpts/s, 3 updates/pt/step); "
                     "input %.3f s, context %.3f s, total %.3f s\n",

@@ -112,6 +112,17 @@ int fdw_read_input_stencil(const char *path, fdw_input *out);
  * (lib/cwp/src/par/lib/getpars.c:447-453). */
 int fdw_read_input_cpu(const char *path, int apply_defaults, fdw_input *out);
 
+/* raw float32 files of the drop-in surface (vpfile, datfile, vel_ext_file, input.bin, dir.image ...).
+ * fdw_read_floats: like the reference's fread calls a short file leaves the rest of dst untouched; returns the
+ * number of floats read, -1 when the file cannot be opened.  fdw_write_floats: append != 0 appends (the shot loop of
+ * mod_main.cpp:163-166 writes datfile shot by shot); FDW_ERR_IO on failure. */
+long long fdw_read_floats(const char *path, float *dst, long long n);
+int fdw_write_floats(const char *path, const float *src, long long n, int append);
+/* one shot of the image stack as rtm_code keeps it (fd-code.cu:521-528): img[ix][iz] += imloc[ix][iz] in the
+ * reference's loop order and, when path is not NULL, the text block "======== is ========" followed by one
+ * " %f " line per point appended to image.num (is == 0 truncates the file first). */
+int fdw_image_stack_shot(const char *path, int is, int nx, int nz, float *img, const float *imloc);
+
 /* ---------------------------------------------------------------- context */
 const char *fdw_last_error(void);
 int fdw_device_count(void);

@@ -75,6 +75,9 @@ SIGNATURES = {
     "fdw_read_input_gpu": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Input)]),
     "fdw_read_input_stencil": (C.c_int, [C.c_char_p, C.POINTER(Input)]),
     "fdw_read_input_cpu": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Input)]),
+    "fdw_read_floats": (C.c_longlong, [C.c_char_p, C.c_void_p, C.c_longlong]),
+    "fdw_write_floats": (C.c_int, [C.c_char_p, C.c_void_p, C.c_longlong, C.c_int]),
+    "fdw_image_stack_shot": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fdw_last_error": (C.c_char_p, []),
     "fdw_device_count": (C.c_int, []),
     "fdw_create": (C.c_int, [C.POINTER(Params), C.POINTER(C.c_void_p)]),

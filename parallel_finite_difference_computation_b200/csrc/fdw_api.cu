@@ -157,10 +157,11 @@ struct fdw_ctx {
     int use_graph = 1;
     long long graph_replays = 0;
     int use_multirect = 1;       /* the sponge strips of a level in ONE launch (FDW_MULTIRECT=0: one launch per strip) */
-    /* single-GPU level loop as a replayed CUDA graph (pairs of levels, node arguments refreshed): grids whose level
-     * is tens of microseconds -- above the tile / persistent kernels' range, below the size where two stream-ordered
-     * launches, two event records and two waits per level no longer matter (FDW_LEVEL_GRAPH=0 turns it off) */
-    int level_graph = 1;
+    /* single-GPU level loop as a replayed CUDA graph (pairs of levels, node arguments refreshed), for grids whose
+     * level is tens of microseconds.  OFF by default (FDW_LEVEL_GRAPH=1): measured on the 8272 x 2128 and 8272 x 4176
+     * grids it gains 1 us per level with no sponge strips and LOSES 1.5-6 us with them (the stream-ordered launches
+     * already keep the GPU fed at 60-130 us per level; profiles/r02n_level_graph_and_chunking.log) */
+    int level_graph = 0;
     long long level_graph_limit = 1LL << 25; /* float4 columns x rows */
     /* split-phase step (slab decomposition) */
     bool step_open = false;

@@ -398,3 +398,54 @@ int fdw_read_input_cpu(const char *path, int apply_defaults, fdw_input *in)
     if (apply_defaults) input_defaults(in);
     return FDW_OK;
 }
+
+/* ---- raw float32 files and the image.num text dump of the drop-in surface */
+long long fdw_read_floats(const char *path, float *dst, long long n)
+{
+    if (!path || !dst || n < 0) return -1;
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    size_t got = fread(dst, sizeof(float), (size_t)n, f);
+    fclose(f);
+    return (long long)got;
+}
+
+int fdw_write_floats(const char *path, const float *src, long long n, int append)
+{
+    if (!path || !src || n < 0) return FDW_ERR_ARG;
+    FILE *f = fopen(path, append ? "ab" : "wb");
+    if (!f) {
+        fdw_set_error("cannot open %s for writing", path);
+        return FDW_ERR_IO;
+    }
+    const size_t put = fwrite(src, sizeof(float), (size_t)n, f);
+    if (fclose(f) != 0 || put != (size_t)n) {
+        fdw_set_error("short write to %s", path);
+        return FDW_ERR_IO;
+    }
+    return FDW_OK;
+}
+
+int fdw_image_stack_shot(const char *path, int is, int nx, int nz, float *img, const float *imloc)
+{
+    if (!img || !imloc || nx < 1 || nz < 1) return FDW_ERR_ARG;
+    FILE *f = NULL;
+    if (path) {
+        f = fopen(path, is == 0 ? "w" : "a");
+        if (!f) {
+            fdw_set_error("cannot open %s for writing", path);
+            return FDW_ERR_IO;
+        }
+        fprintf(f, "======== %i ========\n", is);
+    }
+    for (int iz = 0; iz < nz; iz++)
+        for (int ix = 0; ix < nx; ix++) {
+            img[(size_t)ix * nz + iz] += imloc[(size_t)ix * nz + iz];
+            if (f) fprintf(f, " %f \n", img[(size_t)ix * nz + iz]);
+        }
+    if (f && fclose(f) != 0) {
+        fdw_set_error("short write to %s", path);
+        return FDW_ERR_IO;
+    }
+    return FDW_OK;
+}

@@ -45,8 +45,7 @@ def launch_mode(request, monkeypatch):
     if request.param not in ("one-launch", "persistent", "tile"):
         monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
         monkeypatch.setenv("FDW_FORK_LIMIT", "0")
-    if request.param != "level-graph":
-        monkeypatch.setenv("FDW_LEVEL_GRAPH", "0")
+    monkeypatch.setenv("FDW_LEVEL_GRAPH", "1" if request.param == "level-graph" else "0")
     return request.param
 
 
@@ -119,6 +118,7 @@ def test_level_loop_is_a_replayed_graph(lib, monkeypatch):
     monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
     monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
     monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    monkeypatch.setenv("FDW_LEVEL_GRAPH", "1")
     with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=lib) as w:
         w.set_v2(np.full((94, 320), 4.0e6, np.float32))
         w.zero()

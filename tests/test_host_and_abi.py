@@ -134,3 +134,34 @@ def test_cpu_dialect_reader(tmp_path):
     assert (d["nx"], d["nt"], d["ns"], d["order"], d["nxb"], d["nzb"]) == (151, 1001, 1, 8, 40, 40)
     assert d["vpfile"] == "3layer_151x151.bin" and d["datfile"] == "dobs.bin" and d["has_datfile"] == 1
     assert abs(d["fac"] - 0.010) < 1e-9
+
+
+def test_float_files_and_image_num(tmp_path):
+    """the raw float32 readers / writers and the image.num text dump of the drop-in surface live in the library
+    (SURVEY 8f.2): short reads leave the rest of the buffer alone, append mode, the reference's text format
+    (fd-code.cu:521-528: "======== is ========" then " %f " per point, iz outer / ix inner, img += imloc)"""
+    lib = fdw.load()
+    p = str(tmp_path / "a.bin").encode()
+    a = np.arange(7, dtype=np.float32)
+    assert lib.fdw_write_floats(p, a.ctypes.data, 7, 0) == 0
+    assert lib.fdw_write_floats(p, a.ctypes.data, 3, 1) == 0
+    buf = np.full(12, -1.0, np.float32)
+    assert lib.fdw_read_floats(p, buf.ctypes.data, 12) == 10
+    assert np.array_equal(buf, np.concatenate([a, a[:3], [-1.0, -1.0]]).astype(np.float32))
+    assert lib.fdw_read_floats(str(tmp_path / "missing.bin").encode(), buf.ctypes.data, 12) == -1
+    assert lib.fdw_write_floats(str(tmp_path / "no_dir" / "x.bin").encode(), a.ctypes.data, 7, 0) == -4
+    nx, nz = 3, 2
+    img = np.zeros((nx, nz), np.float32)
+    num = str(tmp_path / "image.num").encode()
+    want = ""
+    acc = np.zeros((nx, nz), np.float32)
+    for is_ in range(2):
+        imloc = (np.arange(nx * nz, dtype=np.float32).reshape(nx, nz) + 0.5) * (is_ + 1)
+        assert lib.fdw_image_stack_shot(num, is_, nx, nz, img.ctypes.data, imloc.ctypes.data) == 0
+        acc += imloc
+        want += "======== %i ========\n" % is_
+        for iz in range(nz):
+            for ix in range(nx):
+                want += " %f \n" % acc[ix, iz]
+    assert np.array_equal(img, acc)
+    assert open(num.decode()).read() == want
