@@ -156,6 +156,14 @@ struct fdw_ctx {
     std::vector<RecLaunch> lshape;         /* the launch list the graph was built from */
     int use_graph = 1;
     long long graph_replays = 0;
+    /* The replayed graph pays off where the HOST is the limit -- a slab level of a few tens of microseconds against
+     * ~12 driver calls; above that, stream-ordered launches are faster on the device (measured on 2 B200s, 4136 x
+     * 2128 slabs, us per level mod_main / rtm backward: graph 54.5 / 71.2, direct 48.4 / 62.1;
+     * profiles/r02q_slab2_sweep.log).  graph_limit: float4 columns x rows below which the slab loop is replayed
+     * (FDW_GRAPH_LIMIT); graph_levels: levels per graph launch (FDW_GRAPH_LEVELS, even) -- a launch every 2 levels
+     * costs a thin slab a start-up gap every ~45 us */
+    long long graph_limit = 1LL << 21;
+    int graph_levels = 8;
     int use_multirect = 1;       /* the sponge strips of a level in ONE launch (FDW_MULTIRECT=0: one launch per strip) */
     /* single-GPU level loop as a replayed CUDA graph (pairs of levels, node arguments refreshed), for grids whose
      * level is tens of microseconds.  OFF by default (FDW_LEVEL_GRAPH=1): measured on the 8272 x 2128 and 8272 x 4176
@@ -1120,6 +1128,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_LEVEL_GRAPH")) c->level_graph = atoi(e);
     if (const char *e = getenv("FDW_LEVEL_GRAPH_LIMIT")) c->level_graph_limit = atoll(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);
+    if (const char *e = getenv("FDW_GRAPH_LIMIT")) c->graph_limit = atoll(e);
+    if (const char *e = getenv("FDW_GRAPH_LEVELS")) { c->graph_levels = atoi(e) & ~1; if (c->graph_levels < 2) c->graph_levels = 2; }
     if (const char *e = getenv("FDW_FUSE_FLAGS")) c->fuse_flags = atoi(e);
     if (const char *e = getenv("FDW_TIMEOUT_MS")) c->timeout_ns = 1000000ull * (unsigned long long)atoll(e);
 
@@ -2225,13 +2235,13 @@ static int graph_build(fdw_ctx *c, std::vector<RecLaunch> &rec)
     return FDW_OK;
 }
 
-/* two levels (it, it+1): record, then build or refresh the graph and launch it */
-static int peer_level_pair_graph(fdw_ctx *c, int it)
+/* nlev levels (an even number: the buffers alternate) from `it`: record, then build or refresh the graph and launch it */
+static int peer_levels_graph(fdw_ctx *c, int it, int nlev)
 {
     std::vector<RecLaunch> rec;
     c->rec = &rec;
     int rc = FDW_OK;
-    for (int l = 0; l < 2 && rc == FDW_OK; l++) { c->rec_level = l; rc = peer_level(c, it + l); }
+    for (int l = 0; l < nlev && rc == FDW_OK; l++) { c->rec_level = l; rc = peer_level(c, it + l); }
     c->rec = nullptr;
     CHECK(rc);
     return graph_submit(c, rec);
@@ -2326,10 +2336,11 @@ extern "C" int fdw_peer_levels(fdw_ctx *c, int it0, int nsteps)
     if (try_pslab(c, it0, nsteps)) return FDW_OK;
     int it = it0;
     const int end = it0 + nsteps;
-    if (c->use_graph && nsteps >= 6) {
+    if (c->use_graph && nsteps >= 6 && (long long)c->ncol4 * c->nloc < c->graph_limit) {
         /* the first two levels directly (their sponge bookkeeping differs from the steady state) */
         for (int k = 0; k < 2; k++) CHECK(peer_level(c, it++));
-        while (end - it >= 2) { CHECK(peer_level_pair_graph(c, it)); it += 2; }
+        const int g = end - it >= c->graph_levels ? c->graph_levels : 2;
+        while (end - it >= g) { CHECK(peer_levels_graph(c, it, g)); it += g; }
     }
     while (it < end) CHECK(peer_level(c, it++));
     return FDW_OK;

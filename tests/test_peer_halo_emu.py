@@ -195,10 +195,11 @@ def test_async_local_round_trip_equals_synchronous(emu):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("fuse", ["1", "0"])
-def test_peer_level_loop_graph_replay_threads(emu, world, fuse, monkeypatch):
+@pytest.mark.parametrize("fuse,glevels", [("1", 8), ("0", 8), ("1", 2), ("1", 4)])
+def test_peer_level_loop_graph_replay_threads(emu, world, fuse, glevels, monkeypatch):
     """The whole level loop in ONE fdw_peer_levels call per slab (as on the GPUs): the first two levels are issued
-    directly, every further pair is recorded, turned into a graph and replayed with refreshed node arguments
+    directly, every further group of FDW_GRAPH_LEVELS levels (default 8) is recorded, turned into a graph and
+    replayed with refreshed node arguments, a remainder shorter than a group is issued directly
     (the host stand-in keeps the kernel nodes and runs them in creation order).  Each slab runs in its own host
     thread and the acquire really waits (FDW_EMU_SPIN), so the slabs are coupled only through the flags --
     with the acquire/release inside the boundary kernels (fuse=1) and as stand-alone kernels (fuse=0)."""
@@ -206,9 +207,10 @@ def test_peer_level_loop_graph_replay_threads(emu, world, fuse, monkeypatch):
     monkeypatch.setenv("FDW_EMU_SPIN", "1")
     monkeypatch.setenv("FDW_FUSE_FLAGS", fuse)
     monkeypatch.setenv("FDW_GRAPH", "1")
+    monkeypatch.setenv("FDW_GRAPH_LEVELS", str(glevels))
     monkeypatch.setenv("OMP_NUM_THREADS", "1")
     rng = np.random.default_rng(23)
-    nx, nz, nxb, nzb, nt = 47, 33, 8, 8, 13  # 2 direct levels + 5 graph pairs + 1 direct level
+    nx, nz, nxb, nzb, nt = 47, 33, 8, 8, 21  # 2 direct levels + 19: 2 groups of 8 (+3 direct) / 4 of 4 (+3) / 9 pairs (+1)
     nxe, nze = nx + 2 * nxb, nz + 2 * nzb
     v2 = PC.layered_v2(nx, nz, nxb, nzb, rng)
     a = rng.uniform(-1, 1, (nxe, nze)).astype(np.float32)
@@ -251,7 +253,7 @@ def test_peer_level_loop_graph_replay_threads(emu, world, fuse, monkeypatch):
             t.join(120)
         assert not errors, errors
         assert not any(t.is_alive() for t in threads)
-        assert C.c_longlong.in_dll(emu, "emu_graph_launches").value - launches0 == world * ((nt - 2) // 2)
+        assert C.c_longlong.in_dll(emu, "emu_graph_launches").value - launches0 == world * ((nt - 2) // glevels)
         for r, w in enumerate(slabs):
             x0, x1 = slab_rows(nxe, world, r)
             n = np.zeros((x1 - x0, nze), np.float32)
