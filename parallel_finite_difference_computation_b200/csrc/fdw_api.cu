@@ -160,11 +160,14 @@ struct fdw_ctx {
      * ~12 driver calls; above that, stream-ordered launches are faster on the device (measured on 2 B200s, 4136 x
      * 2128 slabs, us per level mod_main / rtm backward: graph 54.5 / 71.2, direct 48.4 / 62.1;
      * profiles/r02q_slab2_sweep.log).  graph_limit: float4 columns x rows below which the slab loop is replayed
-     * (FDW_GRAPH_LIMIT); graph_levels: levels per graph launch (FDW_GRAPH_LEVELS, even) -- a launch every 2 levels
-     * costs a thin slab a start-up gap every ~45 us */
+     * (FDW_GRAPH_LIMIT); graph_levels: levels per graph launch (FDW_GRAPH_LEVELS, even; 8 or 16 levels per launch
+     * measured no better than 2 -- refreshing 40+ node arguments then takes the host as long as the levels run;
+     * profiles/r02r_slab2_sweep_graph_levels.log) */
     long long graph_limit = 1LL << 21;
-    int graph_levels = 8;
+    int graph_levels = 2;
     int use_multirect = 1;       /* the sponge strips of a level in ONE launch (FDW_MULTIRECT=0: one launch per strip) */
+    int inplace_sponge = 1;      /* mid-size whole grids: pending sponge passes applied in place before a plain launch */
+    long long inplace_limit = 1LL << 25; /* float4 columns x rows below which that is done (FDW_SPONGE_INPLACE_LIMIT) */
     /* single-GPU level loop as a replayed CUDA graph (pairs of levels, node arguments refreshed), for grids whose
      * level is tens of microseconds.  OFF by default (FDW_LEVEL_GRAPH=1): measured on the 8272 x 2128 and 8272 x 4176
      * grids it gains 1 us per level with no sponge strips and LOSES 1.5-6 us with them (the stream-ordered launches
@@ -203,6 +206,37 @@ __global__ void k_materialize(float *r0, long long pitch, int nze, int row_lo, i
     const float xf = (j < tx_jlim) ? tx[lr] : 1.0f;
     for (int c = 0; c < cnt; c++) v = __fmul_rn(__fmul_rn(v, zf), xf);
     r0[(long long)lr * pitch + j] = v;
+}
+
+/* The sponge as an in-place pass over the regions where a factor differs from 1 (up to four rectangles), both
+ * time levels in one launch: what kernel_tapper / taper_apply do, restricted to where it matters.  Used before the
+ * update of a mid-size whole-grid level, so that ONE plain launch covers the whole grid (see sponge_inplace). */
+struct SpongeRects {
+    float *f[2];
+    int cnt[2];
+    long long pitch;
+    int grow0, tx_jlim, tz_ilim, n;
+    const float *tz, *tx;
+    struct { int c0, c1, r0, r1; unsigned e0; } r[4];
+    unsigned total; /* < 2^31 elements (checked by the caller) */
+};
+__global__ void k_sponge_inplace(const __grid_constant__ SpongeRects a)
+{
+    unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.total) return;
+    int k = 0;
+    while (k + 1 < a.n && e >= a.r[k + 1].e0) k++;
+    e -= a.r[k].e0;
+    const unsigned w = (unsigned)(a.r[k].c1 - a.r[k].c0);
+    const int lr = a.r[k].r0 + (int)(e / w), j = a.r[k].c0 + (int)(e % w);
+    const float zf = (a.grow0 + lr < a.tz_ilim) ? a.tz[j] : 1.0f;
+    const float xf = (j < a.tx_jlim) ? a.tx[lr] : 1.0f;
+    for (int s = 0; s < 2; s++) {
+        if (!a.f[s] || a.cnt[s] <= 0) continue;
+        float v = a.f[s][(long long)lr * a.pitch + j];
+        for (int c = 0; c < a.cnt[s]; c++) v = __fmul_rn(__fmul_rn(v, zf), xf);
+        a.f[s][(long long)lr * a.pitch + j] = v;
+    }
 }
 
 /* peer-memory halo exchange: release / acquire of the "boundary rows delivered" counters.  The
@@ -251,6 +285,7 @@ static void thunk_peer_wait(void **a)
     k_peer_wait(*(const unsigned **)a[0], *(unsigned *)a[1], *(int *)a[2], *(int *)a[3], *(int **)a[4], *(unsigned long long *)a[5]);
 }
 static void thunk_scale_rows(void **a) { k_scale_rows(*(float **)a[0], *(long long *)a[1], *(float *)a[2]); }
+static void thunk_sponge_inplace(void **a) { k_sponge_inplace(*(const SpongeRects *)a[0]); }
 static void thunk_materialize(void **a)
 {
     k_materialize(*(float **)a[0], *(long long *)a[1], *(int *)a[2], *(int *)a[3], *(int *)a[4], *(int *)a[5],
@@ -680,6 +715,8 @@ static void set_source_args(const fdw_ctx *c, StepArgs *a, int it)
     a->src_amp = (it >= 0 && it < (int)c->wavelet.size()) ? c->wavelet[it] : 0.0f;
 }
 
+static int sponge_inplace(fdw_ctx *c, Field &n, Field &o, int epi);
+
 /* one propagation step of `pair` with the context's sponge and step ordering.
  * fill(a) lets the caller add epilogue arguments. */
 template <class Fill>
@@ -691,6 +728,7 @@ static int step_pair(fdw_ctx *c, int pair, int recipe, int epi, bool sponge, boo
         n.pend++;
         o.pend++;
     }
+    if (n.pend || o.pend) CHECK(sponge_inplace(c, n, o, epi)); /* mid-size whole grids: pending passes applied in place */
     StepArgs a;
     base_args(c, pair, &a);
     a.taper_on = (n.pend || o.pend) ? 1 : 0;
@@ -975,6 +1013,58 @@ static int materialize(fdw_ctx *c, Field &f)
     return FDW_OK;
 }
 
+/* Mid-size whole-grid levels (tens of microseconds: the 8272 x 2128 mod_main grid, the 8272 x 4176 RTM grid): the
+ * sponge-on-load strips cost more than they hide -- 6-10 % of the points on the 110-register instantiation, resident
+ * from the start of the level, take the bulk launch's occupancy away (measured: four-sided sponge +15 us on a 61 us
+ * level even as one folded multi-rectangle launch).  There the pending sponge passes are applied IN PLACE to the
+ * sponge regions of both levels first (one launch of an element-wise kernel over ~5 % of the grid: ~12 MB of
+ * traffic against 280 MB for the level) and ONE plain launch then covers the whole grid.  Same multiplications in
+ * the same order as on load (and as the reference's own in-place passes), so the bits do not change.  Not used
+ * where a level goes out in pieces (slabs), on small grids (one sponge-kernel launch), on large ones (a strip hides
+ * behind a 0.7 ms bulk launch for free), nor when a recorded seismogram sample would need a non-unit factor of the
+ * pass that is still to come (receivers inside the sponge). */
+static int sponge_inplace(fdw_ctx *c, Field &n, Field &o, int epi)
+{
+    const long long work = (long long)c->ncol4 * c->nloc;
+    if (!c->inplace_sponge || c->rec || c->step_open || c->gx0 != 0 || c->nloc != c->nxe ||
+        work < c->small_grid_limit || work >= c->inplace_limit)
+        return FDW_OK;
+    if ((epi & fdw::EPI_RECORD) && !(c->shot_gz >= c->tap_jlo && c->shot_gz < c->tap_jhi)) return FDW_OK;
+    if (epi & fdw::EPI_PUSH) return FDW_OK;
+    SpongeRects a;
+    memset(&a, 0, sizeof a);
+    a.f[0] = n.pend ? n.r0 : nullptr; a.cnt[0] = n.pend;
+    a.f[1] = o.pend ? o.r0 : nullptr; a.cnt[1] = o.pend;
+    a.pitch = c->pitch; a.grow0 = c->gx0; a.tx_jlim = c->tx_jlim; a.tz_ilim = c->tz_ilim;
+    a.tz = c->tz; a.tx = c->tx;
+    const int jlo = c->tap_jlo > INT_MIN ? (c->tap_jlo < c->nze ? c->tap_jlo : c->nze) : 0;
+    const int jhi = c->tap_jhi < INT_MAX ? (c->tap_jhi > jlo ? c->tap_jhi : jlo) : c->nze;
+    const int ilo = c->tap_ilo > INT_MIN ? (c->tap_ilo < c->nloc ? c->tap_ilo : c->nloc) : 0;
+    const int ihi = c->tap_ihi < INT_MAX ? (c->tap_ihi > ilo ? c->tap_ihi : ilo) : c->nloc;
+    const int rects[4][4] = {{0, jlo, 0, c->nloc}, {jhi, c->nze, 0, c->nloc}, {jlo, jhi, 0, ilo}, {jlo, jhi, ihi, c->nloc}};
+    long long total = 0;
+    for (int k = 0; k < 4; k++) {
+        if (rects[k][1] <= rects[k][0] || rects[k][3] <= rects[k][2]) continue;
+        a.r[a.n].c0 = rects[k][0]; a.r[a.n].c1 = rects[k][1]; a.r[a.n].r0 = rects[k][2]; a.r[a.n].r1 = rects[k][3];
+        a.r[a.n].e0 = (unsigned)total;
+        total += (long long)(rects[k][1] - rects[k][0]) * (rects[k][3] - rects[k][2]);
+        a.n++;
+    }
+    if (total >= 0x7fffffffLL) return FDW_OK; /* (the strips do it) */
+    a.total = (unsigned)total;
+    if (total > 0) {
+        const int threads = 256;
+        const long long blocks = (total + threads - 1) / threads;
+        void *params[] = {&a};
+        CU(cudaLaunchKernel(FDW_KPTR(k_sponge_inplace, thunk_sponge_inplace), dim3((unsigned)blocks), dim3(threads), params, 0,
+                            c->stream));
+        c->launches++;
+    }
+    n.pend = 0;
+    o.pend = 0;
+    return FDW_OK;
+}
+
 static int field_alloc(fdw_ctx *c, Field *f)
 {
     CU(cudaMalloc(&f->base, c->field_elems * sizeof(float)));
@@ -1125,6 +1215,8 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
     if (const char *e = getenv("FDW_RPC_RULE")) g_rpc_rule = atoi(e);
     if (const char *e = getenv("FDW_MULTIRECT")) c->use_multirect = atoi(e);
+    if (const char *e = getenv("FDW_SPONGE_INPLACE")) c->inplace_sponge = atoi(e);
+    if (const char *e = getenv("FDW_SPONGE_INPLACE_LIMIT")) c->inplace_limit = atoll(e);
     if (const char *e = getenv("FDW_LEVEL_GRAPH")) c->level_graph = atoi(e);
     if (const char *e = getenv("FDW_LEVEL_GRAPH_LIMIT")) c->level_graph_limit = atoll(e);
     if (const char *e = getenv("FDW_GRAPH")) c->use_graph = atoi(e);

@@ -166,12 +166,12 @@ def case_gpu_rtm(lib, nx=41, nz=33, nxb=8, nzb=8, nt=60, compat=True, seed=5, ho
 
 
 # ------------------------------------------------------------------ CPU family programs
-def case_mod_shot(lib, nx=33, nz=27, nxb=7, nzb=6, nt=50, seed=9, order=8):
+def case_mod_shot(lib, nx=33, nz=27, nxb=7, nzb=6, nt=50, seed=9, order=8, gz=None):
     rng = np.random.default_rng(seed)
     dx, dz, dt, fac, fpeak = 10.0, 10.0, 0.001, 0.05, 35.0
     v2 = layered_v2(nx, nz, nxb, nzb, rng)
     srce = O.ricker_wavelet(nt, dt, fpeak, O.FAM_C)
-    sx, sz, gz = nxb + 2, nzb, nzb
+    sx, sz, gz = nxb + 2, nzb, (nzb if gz is None else gz)
     cfg = O.CpuCfg(order, nx, nz, nxb, nzb, nt, dx, dz, dt, fac)
     want = O.mod_shot(cfg, v2, srce, sx, sz, gz)
     with Wave2D(nx, nz, nxb, nzb, dx, dz, dt, order=order, fac=fac, family=FAMILY_CPU, taper=TAPER_FOUR, nt=nt,

@@ -15,7 +15,7 @@ def emu():
     return load_emu()
 
 
-@pytest.fixture(params=["persistent", "one-launch", "rectangles", "rectangles+fork", "level-graph"])
+@pytest.fixture(params=["persistent", "one-launch", "rectangles", "rectangles+fork", "level-graph", "inplace-sponge"])
 def launch_mode(request, monkeypatch):
     """the library picks one sponge-kernel launch for tiny grids and plain/sponge rectangles
     (optionally forked to a side stream) for large ones, issued directly or -- mid-size grids -- as a replayed CUDA
@@ -26,6 +26,8 @@ def launch_mode(request, monkeypatch):
         monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
         monkeypatch.setenv("FDW_FORK_LIMIT", "0" if request.param != "rectangles" else str(1 << 40))
     monkeypatch.setenv("FDW_LEVEL_GRAPH", "1" if request.param == "level-graph" else "0")
+    # inplace-sponge: what mid-size whole grids get -- pending sponge passes applied in place, then ONE plain launch
+    monkeypatch.setenv("FDW_SPONGE_INPLACE", "1" if request.param == "inplace-sponge" else "0")
     return request.param
 
 
@@ -104,6 +106,7 @@ def test_level_loop_is_a_replayed_graph(emu, monkeypatch):
     monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
     monkeypatch.setenv("FDW_FORK_LIMIT", "0")
     monkeypatch.setenv("FDW_LEVEL_GRAPH", "1")
+    monkeypatch.setenv("FDW_SPONGE_INPLACE", "0")
     with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=emu) as w:
         w.set_v2(np.full((94, 320), 4.0e6, np.float32))
         w.zero()
@@ -126,6 +129,7 @@ def test_sponge_strips_share_one_launch(emu, multirect, monkeypatch):
     monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
     monkeypatch.setenv("FDW_FORK_LIMIT", "0")
     monkeypatch.setenv("FDW_MULTIRECT", multirect)
+    monkeypatch.setenv("FDW_SPONGE_INPLACE", "0")
     PC.case_advance(emu, FAMILY_CPU, RECIPE_C, TAPER_FOUR, nx=70, nz=300, nxb=12, nzb=10, nt=6, src_kind=SRC_GAUSS7)
     with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=emu) as w:
         w.set_v2(np.full((94, 320), 4.0e6, np.float32))
@@ -134,6 +138,28 @@ def test_sponge_strips_share_one_launch(emu, multirect, monkeypatch):
         w.advance(0, 4)
         # level 0 has no sponge pass pending yet (CPU family: update, then sponge): one launch
         assert w.launch_count() - n0 == (1 + 3 * 2 if multirect == "1" else 1 + 3 * 5)
+
+
+def test_sponge_in_place_then_one_plain_launch(emu, monkeypatch):
+    """mid-size whole grids: the pending sponge passes are applied in place on the sponge regions (one element-wise
+    launch for both levels), then ONE plain launch covers the grid -- 2 launches per level; same bits (the
+    inplace-sponge launch mode runs every advance / shot case this way); receivers inside the sponge keep the strips"""
+    from parallel_finite_difference_computation_b200 import Wave2D
+    monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
+    monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+    monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    monkeypatch.setenv("FDW_SPONGE_INPLACE", "1")
+    monkeypatch.setenv("FDW_TILE", "0")
+    PC.case_advance(emu, FAMILY_CPU, RECIPE_C, TAPER_FOUR, nx=70, nz=300, nxb=12, nzb=10, nt=6, src_kind=SRC_GAUSS7)
+    PC.case_advance(emu, FAMILY_GPU, RECIPE_G, TAPER_TOP, nx=70, nz=300, nxb=12, nzb=10, nt=6, compat=True)
+    with Wave2D(70, 300, 12, 10, 10.0, 10.0, 0.001, family=FAMILY_CPU, recipe=RECIPE_C, taper=TAPER_FOUR, lib=emu) as w:
+        w.set_v2(np.full((94, 320), 4.0e6, np.float32))
+        w.zero()
+        n0 = w.launch_count()
+        w.advance(0, 4)
+        assert w.launch_count() - n0 == 1 + 3 * 2
+    PC.case_mod_shot(emu, nx=40, nz=60, nxb=8, nzb=9)  # gz = nzb: receivers just outside the sponge -> in place
+    PC.case_mod_shot(emu, nx=40, nz=60, nxb=8, nzb=9, gz=4)  # receivers inside the sponge -> strips, sample after the pass
 
 
 @pytest.mark.parametrize("order", [10, 12, 16])
