@@ -156,16 +156,21 @@ struct fdw_ctx {
     std::vector<RecLaunch> lshape;         /* the launch list the graph was built from */
     int use_graph = 1;
     long long graph_replays = 0;
-    /* The replayed graph pays off where the HOST is the limit -- a slab level of a few tens of microseconds against
-     * ~12 driver calls; above that, stream-ordered launches are faster on the device (measured on 2 B200s, 4136 x
-     * 2128 slabs, us per level mod_main / rtm backward: graph 54.5 / 71.2, direct 48.4 / 62.1;
-     * profiles/r02q_slab2_sweep.log).  graph_limit: float4 columns x rows below which the slab loop is replayed
-     * (FDW_GRAPH_LIMIT); graph_levels: levels per graph launch (FDW_GRAPH_LEVELS, even; 8 or 16 levels per launch
-     * measured no better than 2 -- refreshing 40+ node arguments then takes the host as long as the levels run;
+    /* The replayed graph pays off where the HOST is the limit: ~12 driver calls per slab level from each of N
+     * processes.  Measured: 8 B200s, 16384^2 per GPU, per-level cost of the slab machinery over one GPU: +21 us
+     * replayed (round 1), +35 us with direct launches (profiles/r02t_bench_line_n8_direct_launches.json); the
+     * 16384^2 grid cut over 8 GPUs: 121 us per level replayed, 126-136 direct.  On 2 GPUs with 4136 x 2128 slabs the
+     * two are within the run-to-run noise of each other (profiles/r02q_, r02r_slab2_sweep*.log).  So the slab loop is
+     * always replayed; graph_limit (float4 columns x rows, FDW_GRAPH_LIMIT) can restrict that to thin slabs.
+     * graph_levels: levels per graph launch (FDW_GRAPH_LEVELS, even; 8 or 16 levels per launch measured no better
+     * than 2 -- refreshing 40+ node arguments then takes the host as long as the levels run;
      * profiles/r02r_slab2_sweep_graph_levels.log) */
-    long long graph_limit = 1LL << 21;
+    long long graph_limit = 1LL << 62;
     int graph_levels = 2;
     int use_multirect = 1;       /* the sponge strips of a level in ONE launch (FDW_MULTIRECT=0: one launch per strip) */
+    int use_pdl = 1;             /* programmatic dependent launch of the step kernels (FDW_PDL=0: plain launches) */
+    bool pdl_now = false;        /* set around launches that follow their predecessor kernel directly in ONE stream (no
+                                  * fork / join events, no slab boundary chain): only there is the attribute used */
     int inplace_sponge = 1;      /* mid-size whole grids: pending sponge passes applied in place before a plain launch */
     long long inplace_limit = 1LL << 25; /* float4 columns x rows below which that is done (FDW_SPONGE_INPLACE_LIMIT) */
     /* single-GPU level loop as a replayed CUDA graph (pairs of levels, node arguments refreshed), for grids whose
@@ -222,6 +227,8 @@ struct SpongeRects {
 };
 __global__ void k_sponge_inplace(const __grid_constant__ SpongeRects a)
 {
+    fdw::pdl_trigger();
+    fdw::pdl_wait();
     unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= a.total) return;
     int k = 0;
@@ -297,6 +304,10 @@ static void thunk_materialize(void **a)
 #endif
 
 /* ------------------------------------------------------------------ helpers */
+/* launch of a kernel that begins with pdl_wait() (the step kernels, the in-place sponge pass): with programmatic
+ * dependent launch its CTAs may be scheduled while the previous kernel of the stream drains (FDW_PDL=0: off) */
+static cudaError_t launch_pdl(const fdw_ctx *c, const void *k, dim3 grid, dim3 block, void **params, cudaStream_t st);
+
 static const void *step_kernel(int order, int recipe, int epi, int sponge)
 {
     switch (order) {
@@ -513,6 +524,24 @@ static void base_args(const fdw_ctx *c, int pair, StepArgs *a)
  * bulk launch instead of serialising behind it. */
 struct Rect { int c0, c1, r0, r1, sponge; };
 
+static cudaError_t launch_pdl(const fdw_ctx *c, const void *k, dim3 grid, dim3 block, void **params, cudaStream_t st)
+{
+#ifndef FDW_EMU
+    if (c->use_pdl && c->pdl_now) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        memset(at, 0, sizeof at);
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelExC(&cfg, k, params);
+    }
+#endif
+    return cudaLaunchKernel(k, grid, block, params, 0, st);
+}
+
 static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, const Rect &rc, cudaStream_t st)
 {
     if (rc.c1 <= rc.c0 || rc.r1 <= rc.r0) return FDW_OK;
@@ -537,7 +566,8 @@ static int launch_rect(fdw_ctx *c, const StepArgs &base, int recipe, int epi, co
         return FDW_OK;
     }
     void *params[] = {&a};
-    CU(cudaLaunchKernel(k, grid, block, params, 0, st));
+    if (epi & fdw::EPI_PUSH) CU(cudaLaunchKernel(k, grid, block, params, 0, st)); /* boundary chain: acquire / release inside */
+    else CU(launch_pdl(c, k, grid, block, params, st));
     return FDW_OK;
 }
 
@@ -601,7 +631,7 @@ static int launch_rects(fdw_ctx *c, const StepArgs &base, int recipe, int epi, c
         return FDW_OK;
     }
     void *params[] = {&a};
-    CU(cudaLaunchKernel(k, grid, block, params, 0, st));
+    CU(launch_pdl(c, k, grid, block, params, st));
     return FDW_OK;
 }
 
@@ -676,6 +706,7 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
     bool any_side = false;
     for (int k = 0; k < nside; k++) any_side = any_side || (side[k].c1 > side[k].c0 && side[k].r1 > side[k].r0);
     const bool do_fork = fork && any_side;
+    c->pdl_now = !do_fork && !c->step_open && !c->rec;
     cudaStream_t ss = do_fork ? c->side : st;
     const bool ev = do_fork && !c->rec; /* a recorded level gets its fork/join as graph edges instead */
     if (ev) {
@@ -686,17 +717,19 @@ static int launch_level(fdw_ctx *c, const StepArgs &base, int recipe, int epi, i
     if (c->use_multirect && nside > 0) {
         const int rc = launch_rects(c, base, recipe, epi, side, nside, ss);
         if (rc == FDW_OK) nside = 0; /* all strips are in flight */
-        else if (rc != FDW_ERR_UNSUPPORTED) { c->rec_lane = -1; return rc; }
+        else if (rc != FDW_ERR_UNSUPPORTED) { c->rec_lane = -1; c->pdl_now = false; return rc; }
     }
     for (int k = 0; k < nside; k++) {
         if (c->rec && do_fork) c->rec_par = 1; /* disjoint rectangles of one level */
         int rc = launch_rect(c, base, recipe, epi, side[k], ss);
         c->rec_par = 0;
-        if (rc != FDW_OK) { c->rec_lane = -1; return rc; }
+        if (rc != FDW_OK) { c->rec_lane = -1; c->pdl_now = false; return rc; }
     }
     c->rec_lane = -1;
     if (ev) CU(cudaEventRecord(c->ev_join, ss));
-    CHECK(launch_rect(c, base, recipe, epi, bulk, st));
+    const int rcb = launch_rect(c, base, recipe, epi, bulk, st);
+    c->pdl_now = false;
+    CHECK(rcb);
     if (ev) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     return FDW_OK;
 }
@@ -1056,8 +1089,11 @@ static int sponge_inplace(fdw_ctx *c, Field &n, Field &o, int epi)
         const int threads = 256;
         const long long blocks = (total + threads - 1) / threads;
         void *params[] = {&a};
-        CU(cudaLaunchKernel(FDW_KPTR(k_sponge_inplace, thunk_sponge_inplace), dim3((unsigned)blocks), dim3(threads), params, 0,
-                            c->stream));
+        c->pdl_now = true; /* whole-grid level in one stream: in-place pass, plain launch, in-place pass, ... */
+        const cudaError_t le = launch_pdl(c, FDW_KPTR(k_sponge_inplace, thunk_sponge_inplace), dim3((unsigned)blocks),
+                                          dim3(threads), params, c->stream);
+        c->pdl_now = false;
+        CU(le);
         c->launches++;
     }
     n.pend = 0;
@@ -1215,6 +1251,7 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
     if (const char *e = getenv("FDW_RPC_RULE")) g_rpc_rule = atoi(e);
     if (const char *e = getenv("FDW_MULTIRECT")) c->use_multirect = atoi(e);
+    if (const char *e = getenv("FDW_PDL")) c->use_pdl = atoi(e);
     if (const char *e = getenv("FDW_SPONGE_INPLACE")) c->inplace_sponge = atoi(e);
     if (const char *e = getenv("FDW_SPONGE_INPLACE_LIMIT")) c->inplace_limit = atoll(e);
     if (const char *e = getenv("FDW_LEVEL_GRAPH")) c->level_graph = atoi(e);

@@ -247,6 +247,20 @@ FDW_HD unsigned long long wall_ns()
 FDW_HD unsigned long long wall_ns() { return 0; }
 #endif
 
+/* ---- programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+ * attribute may have its CTAs scheduled while the previous kernel of the stream drains; pdl_wait() -- before the
+ * first global access -- blocks until that kernel has completed and its writes are visible; pdl_trigger() tells the
+ * scheduler that the NEXT kernel's CTAs may be scheduled once every CTA of this one has started.  Both are no-ops in
+ * a launch without the attribute.  On grids whose level is tens of microseconds this hides the launch gap and the
+ * ramp-up behind the previous launch's tail. */
+#ifdef __CUDA_ARCH__
+FDW_HD void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+FDW_HD void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+FDW_HD void pdl_wait() {}
+FDW_HD void pdl_trigger() {}
+#endif
+
 /* ---- packed FP32x2 arithmetic (sm_100a FMUL2 / FFMA2: two IEEE round-to-nearest results per
  * instruction, each lane rounded exactly like the scalar FMUL / FADD, so the reference's --fmad=false
  * bit pattern is kept while the FP32 issue slots halve).  ptxas contracts mul.rn.f32x2 + add.rn.f32x2
