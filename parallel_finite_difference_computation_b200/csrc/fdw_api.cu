@@ -172,7 +172,7 @@ struct fdw_ctx {
     bool pdl_now = false;        /* set around launches that follow their predecessor kernel directly in ONE stream (no
                                   * fork / join events, no slab boundary chain): only there is the attribute used */
     int inplace_sponge = 1;      /* mid-size whole grids: pending sponge passes applied in place before a plain launch */
-    long long inplace_limit = 1LL << 25; /* float4 columns x rows below which that is done (FDW_SPONGE_INPLACE_LIMIT) */
+    long long inplace_limit = 1LL << 62; /* float4 columns x rows below which that is done (FDW_SPONGE_INPLACE_LIMIT) */
     /* single-GPU level loop as a replayed CUDA graph (pairs of levels, node arguments refreshed), for grids whose
      * level is tens of microseconds.  OFF by default (FDW_LEVEL_GRAPH=1): measured on the 8272 x 2128 and 8272 x 4176
      * grids it gains 1 us per level with no sponge strips and LOSES 1.5-6 us with them (the stream-ordered launches
@@ -750,6 +750,7 @@ static void set_source_args(const fdw_ctx *c, StepArgs *a, int it)
 
 static int sponge_inplace(fdw_ctx *c, Field &n, Field &o, int epi);
 
+
 /* one propagation step of `pair` with the context's sponge and step ordering.
  * fill(a) lets the caller add epilogue arguments. */
 template <class Fill>
@@ -1046,16 +1047,18 @@ static int materialize(fdw_ctx *c, Field &f)
     return FDW_OK;
 }
 
-/* Mid-size whole-grid levels (tens of microseconds: the 8272 x 2128 mod_main grid, the 8272 x 4176 RTM grid): the
- * sponge-on-load strips cost more than they hide -- 6-10 % of the points on the 110-register instantiation, resident
- * from the start of the level, take the bulk launch's occupancy away (measured: four-sided sponge +15 us on a 61 us
- * level even as one folded multi-rectangle launch).  There the pending sponge passes are applied IN PLACE to the
- * sponge regions of both levels first (one launch of an element-wise kernel over ~5 % of the grid: ~12 MB of
- * traffic against 280 MB for the level) and ONE plain launch then covers the whole grid.  Same multiplications in
- * the same order as on load (and as the reference's own in-place passes), so the bits do not change.  Not used
- * where a level goes out in pieces (slabs), on small grids (one sponge-kernel launch), on large ones (a strip hides
- * behind a 0.7 ms bulk launch for free), nor when a recorded seismogram sample would need a non-unit factor of the
- * pass that is still to come (receivers inside the sponge). */
+/* Whole-grid levels above the small-grid range: the sponge-on-load strips cost more than they hide -- 6-10 % of a
+ * mid-size grid's points on the 110-register instantiation, resident from the start of the level, take the bulk
+ * launch's occupancy away (measured on the 8272 x 2128 grid: four-sided sponge +15 us on a 61 us level even as one
+ * folded multi-rectangle launch).  Instead the pending sponge passes are applied IN PLACE to the sponge regions of
+ * both levels first (one launch of an element-wise kernel over a few per cent of the grid: ~12 MB of traffic against
+ * 280 MB for that level) and ONE plain launch then covers the whole grid; the two follow each other in one stream,
+ * so programmatic dependent launch applies (launch_pdl).  Same multiplications in the same order as on load (and
+ * as the reference's own in-place passes), so the bits do not change.  Measured: mod_main level 78 -> 72 (-> 68 with
+ * PDL) us; 16384^2 with a top sponge, where the one strip hides behind a 0.68 ms bulk launch: still +0.75 %
+ * (profiles/r02s_, r02u_, r02v_).  Not used where a level goes out in pieces (slabs), on small grids (one
+ * sponge-kernel launch), nor when a recorded seismogram sample would need a non-unit factor of the pass that is
+ * still to come (receivers inside the sponge). */
 static int sponge_inplace(fdw_ctx *c, Field &n, Field &o, int epi)
 {
     const long long work = (long long)c->ncol4 * c->nloc;
