@@ -5,12 +5,15 @@
  *   every wavefield level, the premultiplied velocity fl32(v2*dt2) and the
  *   image share one pitched layout: row = one x index, `pitch` floats per row
  *   (multiple of 32 => every row starts on a 128-byte line, float4 columns are
- *   aligned), nze valid columns followed by >= 4 zero pad columns.  GUARD (4)
- *   guard rows precede and follow the slab's rows: zeros on a physical grid
- *   edge, the neighbour's rows (ghost rows) on a slab edge.
+ *   aligned), nze valid columns followed by >= order/2 zero pad columns.
+ *   AGUARD+1 (9) zero guard rows precede and follow the slab's rows; the
+ *   innermost GUARD (4) of them are the ghost rows a slab edge exchanges with
+ *   its neighbour (zeros on a physical grid edge).
  *   Levels are stored RAW; the sponge multiplications still pending on a level
- *   are counted in Field::pend and applied on load by the step kernel (see
- *   fdw_step_core.h) or materialised in place before an export.
+ *   are counted in Field::pend and either applied on load by the sponge
+ *   instantiation of the step kernel (fdw_step_core.h: small grids, slabs) or
+ *   applied in place to the sponge regions right before the level's plain
+ *   launch (sponge_inplace: whole grids), and before an export.
  */
 #ifdef FDW_EMU
 #include "emu_cuda.h" /* tests/emu: host stand-in for the CUDA runtime, unit tests only */
