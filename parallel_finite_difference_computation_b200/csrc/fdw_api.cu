@@ -228,24 +228,39 @@ struct SpongeRects {
     struct { int c0, c1, r0, r1; unsigned e0; } r[4];
     unsigned total; /* < 2^31 elements (checked by the caller) */
 };
+enum { SPONGE_INPLACE_PER_THREAD = 4 }; /* elements per thread, grid-stride: all loads in flight before the first store */
 __global__ void k_sponge_inplace(const __grid_constant__ SpongeRects a)
 {
     fdw::pdl_trigger();
     fdw::pdl_wait();
-    unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.total) return;
-    int k = 0;
-    while (k + 1 < a.n && e >= a.r[k + 1].e0) k++;
-    e -= a.r[k].e0;
-    const unsigned w = (unsigned)(a.r[k].c1 - a.r[k].c0);
-    const int lr = a.r[k].r0 + (int)(e / w), j = a.r[k].c0 + (int)(e % w);
-    const float zf = (a.grow0 + lr < a.tz_ilim) ? a.tz[j] : 1.0f;
-    const float xf = (j < a.tx_jlim) ? a.tx[lr] : 1.0f;
-    for (int s = 0; s < 2; s++) {
-        if (!a.f[s] || a.cnt[s] <= 0) continue;
-        float v = a.f[s][(long long)lr * a.pitch + j];
-        for (int c = 0; c < a.cnt[s]; c++) v = __fmul_rn(__fmul_rn(v, zf), xf);
-        a.f[s][(long long)lr * a.pitch + j] = v;
+    const unsigned stride = gridDim.x * blockDim.x;
+    float v[SPONGE_INPLACE_PER_THREAD][2], zf[SPONGE_INPLACE_PER_THREAD], xf[SPONGE_INPLACE_PER_THREAD];
+    long long off[SPONGE_INPLACE_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < SPONGE_INPLACE_PER_THREAD; q++) {
+        unsigned e = blockIdx.x * blockDim.x + threadIdx.x + (unsigned)q * stride;
+        off[q] = -1;
+        if (e >= a.total) continue;
+        int k = 0;
+        while (k + 1 < a.n && e >= a.r[k + 1].e0) k++;
+        e -= a.r[k].e0;
+        const unsigned w = (unsigned)(a.r[k].c1 - a.r[k].c0);
+        const int lr = a.r[k].r0 + (int)(e / w), j = a.r[k].c0 + (int)(e % w);
+        zf[q] = (a.grow0 + lr < a.tz_ilim) ? a.tz[j] : 1.0f;
+        xf[q] = (j < a.tx_jlim) ? a.tx[lr] : 1.0f;
+        off[q] = (long long)lr * a.pitch + j;
+        for (int s = 0; s < 2; s++)
+            if (a.f[s] && a.cnt[s] > 0) v[q][s] = a.f[s][off[q]];
+    }
+#pragma unroll
+    for (int q = 0; q < SPONGE_INPLACE_PER_THREAD; q++) {
+        if (off[q] < 0) continue;
+        for (int s = 0; s < 2; s++) {
+            if (!a.f[s] || a.cnt[s] <= 0) continue;
+            float x = v[q][s];
+            for (int c = 0; c < a.cnt[s]; c++) x = __fmul_rn(__fmul_rn(x, zf[q]), xf[q]);
+            a.f[s][off[q]] = x;
+        }
     }
 }
 
@@ -1093,7 +1108,7 @@ static int sponge_inplace(fdw_ctx *c, Field &n, Field &o, int epi)
     a.total = (unsigned)total;
     if (total > 0) {
         const int threads = 256;
-        const long long blocks = (total + threads - 1) / threads;
+        const long long blocks = (total + (long long)threads * SPONGE_INPLACE_PER_THREAD - 1) / ((long long)threads * SPONGE_INPLACE_PER_THREAD);
         void *params[] = {&a};
         c->pdl_now = true; /* whole-grid level in one stream: in-place pass, plain launch, in-place pass, ... */
         const cudaError_t le = launch_pdl(c, FDW_KPTR(k_sponge_inplace, thunk_sponge_inplace), dim3((unsigned)blocks),
