@@ -130,6 +130,7 @@ struct fdw_ctx {
     int use_pslab = 1;                   /* persistent slab kernel for thin slabs (FDW_PSLAB=0: graph-replayed launches) */
     long long pslab_limit = 1LL << 20;   /* float4 columns x rows below which a slab's levels run in one launch */
     long long pslab_launches = 0;
+    int pslab_threads = 0;               /* CTA width of the persistent slab kernel; 0 = chosen per slab (FDW_PSLAB_THREADS: 32..128, multiple of 32) */
     int use_tile = 1;                    /* shared-memory tile kernel for those grids (FDW_TILE=0: L2-resident persistent kernel) */
     int smem_optin = 0;                  /* largest dynamic shared memory per CTA */
     long long persist_launches = 0;
@@ -1268,6 +1269,10 @@ extern "C" int fdw_create(const fdw_params *prm, fdw_ctx **out)
     if (const char *e = getenv("FDW_TILE_LL")) c->use_ll = atoi(e);
     if (const char *e = getenv("FDW_PSLAB")) c->use_pslab = atoi(e);
     if (const char *e = getenv("FDW_PSLAB_LIMIT")) c->pslab_limit = atoll(e);
+    if (const char *e = getenv("FDW_PSLAB_THREADS")) {
+        const int t = atoi(e);
+        if (t >= 32 && t <= 128 && t % 32 == 0) c->pslab_threads = t;
+    }
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, prm->device);
     if (const char *e = getenv("FDW_FORK_LIMIT")) c->fork_limit = atoll(e);
     if (const char *e = getenv("FDW_RPC_RULE")) g_rpc_rule = atoi(e);
@@ -2430,7 +2435,20 @@ static int try_pslab(fdw_ctx *c, int it0, int n)
     const bool source = !c->wavelet.empty() && c->phase != PHASE_RTM_BWD;
     if (source && (it0 < 0 || (size_t)(it0 + n) > c->wavelet.size() || !c->wavelet_d)) return 0;
     const bool tap = c->prm.taper != FDW_TAPER_NONE;
-    const int threads = 128;
+    /* CTA width: the one that keeps the most useful lanes resident -- (fill of the last item column) x (resident
+     * threads at this kernel's register count).  532 float4 columns: 128 threads -> 5 item columns, the last 16 % full,
+     * 512 resident threads per SM; 96 threads -> 6 columns, 92 % full, 576 resident: measured 25.5-26.6 -> 23.9-24.4 us
+     * per mod_main level, 28.1 -> 26.2 backward (profiles/r03b_pslab_threads.log) */
+    int threads = c->pslab_threads;
+    if (threads <= 0) {
+        double best = -1.0;
+        const int cand[3] = {128, 96, 64};
+        for (int i = 0; i < 3; i++) {
+            const int t = cand[i], cols = (nc + t - 1) / t;
+            const double eff = (double)nc / ((double)cols * t) * (double)(cached_occupancy(k, t) * t);
+            if (eff > best * 1.02) { best = eff; threads = t; }
+        }
+    }
     PSlabArgs sa;
     memset(&sa, 0, sizeof sa);
     persist_args(c, 0, base, tap, source, it0, n, c->phase == PHASE_RTM_BWD ? 1 : 0,

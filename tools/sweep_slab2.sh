@@ -14,22 +14,12 @@ for l in sys.stdin:
         print('%-44s mod wall %6.1f dev %6.1f | rtm wall %6.1f fwd dev %6.1f bwd dev %6.1f us/level  pslab launches %s' % ('$label', m['us_per_level'], m['level_loop_us_per_level_device_rank0'], r['us_per_level'], r['forward_level_loop_us_per_level_device_rank0'], r['backward_level_loop_us_per_level_device_rank0'], d['persistent_slab_launches_rank0']))
 " >> $out
 }
-export FDW_C5_NT=${NT:-600}
-echo "# 8192 x 2048 model over 2 GPUs (4136-row slabs)" >> $out
-run "default (direct launches at this size)" A=1
-run "FDW_GRAPH_LIMIT=1e9 (graph, 8 levels)" FDW_GRAPH_LIMIT=1000000000
-run "FDW_GRAPH_LIMIT=1e9 FDW_GRAPH_LEVELS=2" FDW_GRAPH_LIMIT=1000000000 FDW_GRAPH_LEVELS=2
-echo "# 4096 x 2048 model over 2 GPUs (2068-row slabs = the per-GPU slab of the stated model over 4 GPUs)" >> $out
-export FDW_C5_NX=4096
-run "default (graph, 8 levels)" A=1
-run "FDW_GRAPH_LEVELS=2" FDW_GRAPH_LEVELS=2
-run "FDW_GRAPH=0 (direct launches)" FDW_GRAPH=0
-run "FDW_PSLAB_LIMIT=2e6 (persistent slab kernel)" FDW_PSLAB_LIMIT=2000000
-echo "# 2048 x 2048 model over 2 GPUs (1064-row slabs = the per-GPU slab of the stated model over 8 GPUs)" >> $out
+export FDW_C5_NT=${NT:-1500}
+echo "# 2048 x 2048 model over 2 GPUs (1064-row slabs = the per-GPU slab of the stated model over 8 GPUs), persistent slab kernel" >> $out
 export FDW_C5_NX=2048
-run "default (persistent slab kernel)" A=1
-run "FDW_PSLAB=0 (graph, 8 levels)" FDW_PSLAB=0
-run "FDW_PSLAB=0 FDW_GRAPH_LEVELS=2" FDW_PSLAB=0 FDW_GRAPH_LEVELS=2
-run "FDW_PSLAB=0 FDW_GRAPH_LEVELS=16" FDW_PSLAB=0 FDW_GRAPH_LEVELS=16
-run "FDW_PSLAB=0 FDW_GRAPH=0 (direct launches)" FDW_PSLAB=0 FDW_GRAPH=0
+run "128-thread CTAs (default)" A=1
+run "FDW_PSLAB_THREADS=96" FDW_PSLAB_THREADS=96
+run "FDW_PSLAB_THREADS=64" FDW_PSLAB_THREADS=64
+run "128-thread CTAs again" A=1
+run "FDW_PSLAB_THREADS=96 again" FDW_PSLAB_THREADS=96
 cat $out
