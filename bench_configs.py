@@ -378,7 +378,7 @@ def parity_n_vs_1(rank, world, device, halo="p2p", n=4096, nt=40):
     sp.propagate_local(na, nb_, 0, nt)
     torch.cuda.synchronize()
     used = "p2p" if sp.p2p else "nccl"
-    replays = sp.w.graph_replays()
+    replays, pslabs = sp.w.graph_replays(), sp.w.pslab_launches()
     sp.close()
     parts = [None] * world
     dist.all_gather_object(parts, (na, nb_))
@@ -394,7 +394,7 @@ def parity_n_vs_1(rank, world, device, halo="p2p", n=4096, nt=40):
         older = np.concatenate([p[1] for p in parts])
         ok = np.array_equal(newest.view(np.uint32), a.view(np.uint32)) and np.array_equal(older.view(np.uint32), b.view(np.uint32))
         verdict = {"result": "bitwise" if ok else "MISMATCH", "grid": [n, n], "levels": nt, "slabs": world, "halo": used,
-                   "graph_replays_rank0": int(replays)}
+                   "graph_replays_rank0": int(replays), "persistent_slab_launches_rank0": int(pslabs)}
     return verdict
 
 

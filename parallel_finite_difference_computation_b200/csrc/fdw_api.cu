@@ -2442,10 +2442,13 @@ static int try_pslab(fdw_ctx *c, int it0, int n)
     int threads = c->pslab_threads;
     if (threads <= 0) {
         double best = -1.0;
-        const int cand[3] = {128, 96, 64};
-        for (int i = 0; i < 3; i++) {
+        const int cand[2] = {128, 96}; /* (64: more resident lanes still, but twice the CTAs at the level barrier -- measured no gain) */
+        for (int i = 0; i < 2; i++) {
             const int t = cand[i], cols = (nc + t - 1) / t;
             const double eff = (double)nc / ((double)cols * t) * (double)(cached_occupancy(k, t) * t);
+            if (getenv("FDW_PSLAB_VERBOSE"))
+                fprintf(stderr, "fdwave pslab: %d threads -> %d item columns, %d CTAs/SM, %.0f useful lanes/SM\n", t, cols,
+                        cached_occupancy(k, t), eff);
             if (eff > best * 1.02) { best = eff; threads = t; }
         }
     }
