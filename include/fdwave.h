@@ -176,7 +176,10 @@ int fdw_rtm_shot_cpu(fdw_ctx *ctx, int sx, int sz, int gz, const float *dobs_all
  * call order (img += imloc, fd-code.cu:522-528 -- the same single float add per point, so the stack equals the
  * reference's sequential one bit for bit); one download at the end.  All calls are asynchronous; host arrays
  * should be pinned (pageable memory works but serialises). */
-int fdw_v2_stage(fdw_ctx *ctx, const float *v2);  /* whole extended grid [nxe][nze]; must stay valid until commit */
+/* v2: whole extended grid [nxe][nze].  The copy is asynchronous: the array must stay valid and unchanged until it has
+ * completed -- i.e. until a fdw_sync / fdw_stack_download that follows the matching fdw_v2_commit (the compute stream
+ * waits for the copy there); a caller that refills host buffers per shot alternates two of them. */
+int fdw_v2_stage(fdw_ctx *ctx, const float *v2);
 int fdw_v2_commit(fdw_ctx *ctx);                  /* the staged velocity becomes the current one (stream-ordered) */
 /* fd_back (fd-code.cu:290-341) on the levels fdw_forward left on the device; the shot image stays on the device */
 int fdw_backward_device(fdw_ctx *ctx, const float *dobs, int gz);
