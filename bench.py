@@ -347,10 +347,19 @@ def run_ours(args):
         bufs.append((hn, ho, hn.numpy(), ho.numpy()))
     e2e_steps = max(4, min(args.steps, 40))  # K steps like the device-timed leg (the whole 10 000-level job is 40)
 
+    e2e_streams = [stream, stream2] if pipelined and len(props) == 2 else None
+    lv_done = [torch.cuda.Event(), torch.cuda.Event()]
+    serial_levels = os.environ.get("FDW_BENCH_E2E_SERIAL_LEVELS", "1") != "0"
+
     def e2e_job(k, s):
         if pipelined:
             props[k].sync()  # the job issued two steps ago on this propagator has delivered its results
-            props[k].propagate_local_async(bufs[k][2], bufs[k][3], s * LEVELS, LEVELS)
+            if e2e_streams is not None and serial_levels:
+                # the other job's transfers overlap these levels, its level loop does not (see propagate_local_async)
+                props[k].propagate_local_async(bufs[k][2], bufs[k][3], s * LEVELS, LEVELS, stream=e2e_streams[k],
+                                               levels_after=lv_done[1 - k], levels_done=lv_done[k])
+            else:
+                props[k].propagate_local_async(bufs[k][2], bufs[k][3], s * LEVELS, LEVELS)
         else:
             props[k].propagate_local(bufs[k][2], bufs[k][3], s * LEVELS, LEVELS)
 

@@ -343,17 +343,26 @@ class SlabPropagator:
         self.download_local(newest, older)
 
 
-    def propagate_local_async(self, newest, older, it0, nsteps):
+    def propagate_local_async(self, newest, older, it0, nsteps, stream=None, levels_after=None, levels_done=None):
         """propagate_local without the final synchronisation: everything (uploads from the -- pinned --
         host rows, halo refresh, nsteps levels, downloads into the same rows) is enqueued on this
         propagator's stream; call sync() before reading the arrays.  Two propagators on two streams
-        pipeline independent jobs: one's PCIe transfers overlap the other's levels."""
+        pipeline independent jobs: one's PCIe transfers overlap the other's levels.
+
+        stream (the torch stream given to set_stream) + levels_after / levels_done (torch CUDA events): the levels
+        start only after `levels_after` and `levels_done` is recorded behind them, so that two pipelined jobs overlap
+        their TRANSFERS with each other's levels but not their level loops (two grids' step kernels interleaved on one
+        GPU evict each other's halo rows from L2)."""
         if self.world > 1 and not self.p2p:
             raise NotImplementedError("propagate_local_async needs the peer-memory halo exchange (halo='p2p')")
         _lib.check(self.L, self.L.fdw_fields_upload_local(self.h, 0, newest, older))
         if self.world > 1:
             self._peer_refresh()
+        if stream is not None and levels_after is not None:
+            stream.wait_event(levels_after)
         self.advance(it0, nsteps)
+        if stream is not None and levels_done is not None:
+            levels_done.record(stream)
         _lib.check(self.L, self.L.fdw_fields_download_local_async(
             self.h, 0, newest.ctypes.data_as(C.c_void_p), older.ctypes.data_as(C.c_void_p)))
 
