@@ -98,6 +98,21 @@ def test_rtm_main_shot(emu, launch_mode, is_):
     PC.case_rtm_shot_cpu(emu, is_=is_)
 
 
+@pytest.mark.parametrize("threads", ["32", "64", "96", "256"])
+@pytest.mark.parametrize("multirect", ["1", "0"])
+def test_strip_folding_at_every_cta_width(emu, threads, multirect, monkeypatch):
+    """the sponge strips' multi-rectangle launch folds narrow strips to the lane group that pads them least, for
+    whatever CTA width is in force (FDW_THREADS; 96 = a width that is not a power of two), orders 8 and 12"""
+    monkeypatch.setenv("FDW_PERSIST_LIMIT", "0")
+    monkeypatch.setenv("FDW_SMALL_GRID_LIMIT", "0")
+    monkeypatch.setenv("FDW_FORK_LIMIT", "0")
+    monkeypatch.setenv("FDW_SPONGE_INPLACE", "0")
+    monkeypatch.setenv("FDW_THREADS", threads)
+    monkeypatch.setenv("FDW_MULTIRECT", multirect)
+    PC.case_advance(emu, FAMILY_CPU, RECIPE_C, TAPER_FOUR, nx=70, nz=300, nxb=12, nzb=10, nt=5, src_kind=SRC_GAUSS7)
+    PC.case_advance(emu, FAMILY_CPU, RECIPE_C, TAPER_FOUR, order=12, nx=50, nz=200, nxb=12, nzb=10, nt=4)
+
+
 def test_level_loop_is_a_replayed_graph(emu, monkeypatch):
     """a grid above the tile / persistent range: pairs of levels go out as one replayed CUDA graph (arguments
     refreshed per pair), the odd last level directly; bit-exact like every other path (launch_mode level-graph)"""
